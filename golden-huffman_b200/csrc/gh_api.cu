@@ -1,0 +1,182 @@
+// Whole ".crs2" images: what Compressor<CanonicalHuffEncoder<> >::compress() and
+// Decompressor<CanonicalHuffDecoder<> >::decompress() (reference include/compressor.h:62-73, 87-92) do for a
+// file, minus the file I/O. Device-resident variants (kernels only) and host-buffer variants (H2D + kernels + D2H).
+#include <string.h>
+
+#include "gh_common.cuh"
+
+struct gh_ctx {
+  cudaStream_t stream;
+  bool own_stream;
+  uint8_t* d_in;
+  size_t in_cap;
+  uint8_t* d_out;
+  size_t out_cap;
+  void* d_ws;
+  size_t ws_cap;
+  uint64_t* d_small;  // 256 histogram counters + end bit
+  uint8_t* h_small;   // pinned: histogram read-back, header staging
+};
+
+namespace gh {
+
+constexpr size_t kSmallBytes = 4096;
+constexpr size_t kMaxHeader = 1040 + 8 * 32;
+
+static int grow(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return GH_OK;
+  if (*p) GH_CUDA_TRY(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = need + need / 8 + 4096;
+  GH_CUDA_TRY(cudaMalloc(p, want));
+  *cap = want;
+  return GH_OK;
+}
+
+}  // namespace gh
+
+extern "C" {
+
+int gh_ctx_create(gh_ctx** out) {
+  using namespace gh;
+  if (!out) return GH_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return cuda_fail(e);
+  gh_ctx* c = new gh_ctx();
+  memset(c, 0, sizeof(*c));
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&c->d_small), kSmallBytes) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&c->h_small), kSmallBytes) != cudaSuccess) {
+    const int rc = cuda_fail(cudaGetLastError());
+    gh_ctx_destroy(c);
+    return rc;
+  }
+  c->own_stream = true;
+  *out = c;
+  return GH_OK;
+}
+
+int gh_ctx_set_stream(gh_ctx* c, void* stream) {
+  if (!c) return GH_ERR_ARG;
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->own_stream = false;
+  c->stream = (cudaStream_t)stream;
+  return GH_OK;
+}
+
+void gh_ctx_destroy(gh_ctx* c) {
+  if (!c) return;
+  if (c->d_in) cudaFree(c->d_in);
+  if (c->d_out) cudaFree(c->d_out);
+  if (c->d_ws) cudaFree(c->d_ws);
+  if (c->d_small) cudaFree(c->d_small);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int gh_compress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, uint64_t* out_bytes) {
+  using namespace gh;
+  if (!c || !d_out || !out_bytes) return GH_ERR_ARG;
+  if (n == 0) return GH_ERR_EMPTY;
+  if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) return GH_ERR_ARG;
+  // 1. histogram (Encoder::caculate_frequency), counters back to the host
+  int rc = gh_histogram(d_in, n, c->d_small, 0, c->stream);
+  if (rc != GH_OK) return rc;
+  uint64_t* h_hist = reinterpret_cast<uint64_t*>(c->h_small);
+  GH_CUDA_TRY(cudaMemcpyAsync(h_hist, c->d_small, 256 * 8, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  // 2. code + header on the host (gen_encode, write_encode_info)
+  gh_code code;
+  rc = gh_build_code(h_hist, &code);
+  if (rc != GH_OK) return rc;
+  const size_t hdr = gh_header_bytes(&code);
+  const uint64_t bits = gh_payload_bits(&code, h_hist, 1);
+  const uint64_t payload = (bits + 7) / 8;
+  const uint64_t need = (hdr + payload + 3) / 4 * 4;  // the packer stores whole 32-bit words
+  if (cap < need) return GH_ERR_SPACE;
+  uint8_t* h_hdr = c->h_small + 2048;
+  size_t written = 0;
+  rc = gh_write_header(&code, h_hdr, kMaxHeader, &written);
+  if (rc != GH_OK) return rc;
+  // 3. payload (encode_file): the header is 8-byte aligned, the packer wants 16 -> start 64 bits into the vector
+  const size_t base = hdr & ~size_t(15);
+  const uint64_t start_bit = uint64_t(hdr - base) * 8;
+  rc = grow(&c->d_ws, &c->ws_cap, gh_encode_workspace_bytes(n));
+  if (rc != GH_OK) return rc;
+  rc = encode_unchecked(d_in, n, &code, start_bit, 1, d_out + base, (cap - base) / 4 * 4, nullptr, c->d_ws, c->ws_cap,
+                        c->stream);
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(d_out, h_hdr, hdr, cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *out_bytes = hdr + payload;
+  return GH_OK;
+}
+
+int gh_decompress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, uint64_t* out_bytes) {
+  using namespace gh;
+  if (!c || !d_in || !out_bytes || (!d_out && cap)) return GH_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(d_in) & 15) return GH_ERR_ARG;
+  // 1. header (get_encode_info)
+  const size_t peek = n < kMaxHeader ? size_t(n) : kMaxHeader;
+  uint8_t* h_hdr = c->h_small + 2048;
+  GH_CUDA_TRY(cudaMemcpyAsync(h_hdr, d_in, peek, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  gh_code code;
+  size_t hdr = 0;
+  int rc = gh_parse_header(h_hdr, peek, &code, &hdr);
+  if (rc != GH_OK) return rc;
+  if (n <= hdr) return GH_ERR_NO_EOF;
+  // 2. payload (decode_file)
+  const size_t base = hdr & ~size_t(15);
+  const uint64_t slice = n - base;
+  rc = grow(&c->d_ws, &c->ws_cap, gh_decode_workspace_bytes(slice));
+  if (rc != GH_OK) return rc;
+  return decode_full(d_in + base, slice, &code, uint32_t(hdr - base) * 8, d_out, cap, out_bytes, c->d_ws, c->ws_cap,
+                     c->stream);
+}
+
+int gh_compress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+  using namespace gh;
+  if (!c || !out || !out_bytes) return GH_ERR_ARG;
+  if (n == 0) return GH_ERR_EMPTY;
+  if (!in) return GH_ERR_ARG;
+  int rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, n + 16);
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+  // the device image may need up to the full bound; the caller's buffer only has to hold the result
+  const uint64_t bound = gh_compress_bound(n);
+  const uint64_t dev_cap = cap + 16 < bound ? cap + 16 : bound;
+  rc = grow(reinterpret_cast<void**>(&c->d_out), &c->out_cap, dev_cap);
+  if (rc != GH_OK) return rc;
+  uint64_t bytes = 0;
+  rc = gh_compress_device(c, c->d_in, n, c->d_out, c->out_cap, &bytes);
+  if (rc != GH_OK) return rc;
+  if (bytes > cap) return GH_ERR_SPACE;
+  GH_CUDA_TRY(cudaMemcpyAsync(out, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *out_bytes = bytes;
+  return GH_OK;
+}
+
+int gh_decompress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+  using namespace gh;
+  if (!c || !in || !out_bytes || (!out && cap)) return GH_ERR_ARG;
+  int rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, n + 16);
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+  rc = grow(reinterpret_cast<void**>(&c->d_out), &c->out_cap, cap + 16);
+  if (rc != GH_OK) return rc;
+  uint64_t bytes = 0;
+  rc = gh_decompress_device(c, c->d_in, n, c->d_out, cap, &bytes);
+  *out_bytes = bytes;
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(out, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GH_OK;
+}
+
+}  // extern "C"

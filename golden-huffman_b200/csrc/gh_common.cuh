@@ -1,0 +1,76 @@
+// Shared device/host helpers for the sm_100a kernels. Compiled by nvcc for the product
+// (-gencode arch=compute_100a,code=sm_100a); the GH_EMUL branch exists only so tests/emul can run the same
+// kernel logic on the CPU under a pthread shim (test infrastructure, never shipped).
+#ifndef GH_COMMON_CUH_
+#define GH_COMMON_CUH_
+
+#ifndef GH_EMUL
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include "gh_internal.h"
+
+namespace gh {
+
+int cuda_fail(cudaError_t e);  // records the error for gh_last_cuda_error(), returns GH_ERR_CUDA
+void note_launch();            // bumps gh_launch_count()
+// Optional per-kernel timing (gh_profile_enable): CUDA events recorded on the launching stream around a launch.
+void profile_begin(const char* kernel_name, void* stream);
+void profile_end(void* stream);
+int sm_count();                // SMs of the current device (148 on B200)
+int check_launch();            // cudaGetLastError -> status
+
+#define GH_CUDA_TRY(expr)                              \
+  do {                                                 \
+    cudaError_t gh_e_ = (expr);                        \
+    if (gh_e_ != cudaSuccess) return ::gh::cuda_fail(gh_e_); \
+  } while (0)
+
+#ifdef GH_EMUL
+#define GH_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (::gh::note_launch(), gh_emul::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); }))
+#define GH_DYNAMIC_SMEM(name) unsigned char* name = gh_emul::g_block.dyn_smem
+#else
+#define GH_LAUNCH(kernel, grid, block, smem, stream, ...)                              \
+  (::gh::note_launch(), ::gh::profile_begin(#kernel, (void*)(stream)),                  \
+   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__), ::gh::profile_end((void*)(stream)))
+#define GH_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+
+// Stream bytes are one MSB-first bit string: a 32-bit window is the big-endian reading of 4 bytes.
+__device__ __forceinline__ u32 be32(u32 little_endian_word) { return __byte_perm(little_endian_word, 0, 0x0123); }
+
+// 128-bit read-only load (LDG.E.128.CONSTANT)
+__device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
+
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
+
+// inclusive warp scan (Kogge-Stone over shuffles)
+__device__ __forceinline__ u32 warp_inclusive_scan(u32 v, unsigned lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 up = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= unsigned(d)) v += up;
+  }
+  return v;
+}
+
+__device__ __forceinline__ u32 warp_sum(u32 v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+__device__ __forceinline__ u64 warp_sum64(u64 v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+}  // namespace gh
+#endif

@@ -1,0 +1,601 @@
+// K5-K7 -- decode of the reference's unindexed serial bit string (replaces reference
+// include/canonical_huff_encoder.cc:377-419 CanonicalHuffDecoder::decode_file; result-identical to the Fast
+// and Table decoders :422-461, :519-568).
+//
+// The stream has no block boundaries, so codeword boundaries are *discovered* by self-synchronisation
+// (Klein & Wiseman 2003; Weissenberger & Schmidt 2018), arranged here as a fixed-point iteration:
+//
+//   payload = subsequences of S bytes, one thread each (S a multiple of 128, chosen so the grid fills the GPU).
+//   state[i] = (entry_i, count_i, exit_i, eof_i): decoding subsequence i from bit `entry_i` yields count_i symbols
+//              and leaves the subsequence `exit_i` bits into subsequence i+1 (or hits the end mark).
+//   K5a  speculate : every thread decodes its subsequence from entry 0 (entry_0 is the true one).
+//   K5b  sync round: thread i compares entry_i with exit_{i-1}. If they differ it walks BOTH paths in lockstep
+//                    (always stepping the one that is behind) until they meet -- from there on the old result
+//                    is still valid, so only the few symbols up to the meeting point are re-decoded; if they
+//                    never meet inside the subsequence its exit changes and the round is marked dirty.
+//                    Rounds repeat until one is clean; the fixed point is exactly the serial decoder's path
+//                    because entry_0 is exact and every other entry equals its predecessor's exit.
+//                    If many rounds stay dirty (codes that synchronise slowly, e.g. near-fixed-length ones),
+//                    S is multiplied by 4 and the process restarts; at S = whole payload it is the serial walk.
+//   K6   offsets   : first end mark on the true path truncates the counts; exclusive scan -> output offsets.
+//   K7   write     : every thread re-decodes its subsequence from its now-exact entry with the 12-bit LUT
+//                    (long codes: left-justified first_code search, as the reference's Fast decoder does) and
+//                    stores symbols 16 at a time with 128-bit stores.
+//
+// Algorithmic traffic: C bytes read + N bytes written; this implementation reads the payload twice
+// (speculate + write), which the roofline accounting in bench.py does NOT credit.
+#include "gh_common.cuh"
+
+namespace gh {
+
+constexpr int kDecThreads = 256;
+constexpr u32 kNoEof = 0xffffffffu;
+constexpr u32 kMinSubBytes = 128;
+constexpr u32 kMaxSubBytes = 1u << 27;
+constexpr int kRoundsBeforeEscalation = 12;
+
+// per-subsequence state, one 64-bit word so it is read and written atomically
+//   [31:0] count   [47:32] entry   [55:48] exit   [56] eof
+__host__ __device__ inline u64 pack_state(u32 count, u32 entry, u32 exit, u32 eof) {
+  return u64(count) | (u64(entry & 0xffffu) << 32) | (u64(exit & 0xffu) << 48) | (u64(eof & 1u) << 56);
+}
+__host__ __device__ inline u32 st_count(u64 s) { return u32(s); }
+__host__ __device__ inline u32 st_entry(u64 s) { return u32(s >> 32) & 0xffffu; }
+__host__ __device__ inline u32 st_exit(u64 s) { return u32(s >> 48) & 0xffu; }
+__host__ __device__ inline u32 st_eof(u64 s) { return u32(s >> 56) & 1u; }
+
+struct DecControl {  // device-resident, copied back to the host after each round
+  u32 changed;
+  u32 eof_index;  // first subsequence (in order) whose path ends in the end mark
+  u64 total;      // symbols before that end mark
+  u32 exit_bit;
+  u32 eof_found;
+  u32 sub_bytes;
+  u32 pad_;
+  u64 n_sub;
+};
+
+struct DecWorkspace {
+  const DecodeTables* tables;
+  DecControl* ctl;
+  u64* sub;        // [n_sub]
+  u64* tile_sum;   // [n_tiles]
+  u64* tile_base;  // [n_tiles]
+};
+
+struct DecGeometry {
+  const uint8_t* payload;
+  u64 slice_bits;  // bits that belong to this slice
+  u64 readable;    // bytes that may be read from `payload`
+  u32 sub_bytes;
+  u64 n_sub;
+  u32 entry0;
+};
+
+// ---- shared-memory copy of the decode tables --------------------------------------------------------
+struct SmemTables {
+  uint16_t lut[kDecLutSize];
+  u32 first_code_lj[34];
+  u32 start_pos[34];
+  uint16_t symbol[GH_NSYM + 3];
+  u32 max_len;
+};
+
+__device__ __forceinline__ void load_tables(SmemTables& s, const DecodeTables* __restrict__ g) {
+  for (unsigned i = threadIdx.x; i < kDecLutSize / 2; i += blockDim.x)
+    reinterpret_cast<u32*>(s.lut)[i] = reinterpret_cast<const u32*>(g->lut)[i];
+  for (unsigned i = threadIdx.x; i < 34; i += blockDim.x) {
+    s.first_code_lj[i] = g->first_code_lj[i];
+    s.start_pos[i] = g->start_pos[i];
+  }
+  for (unsigned i = threadIdx.x; i < GH_NSYM + 3; i += blockDim.x) s.symbol[i] = g->symbol[i];
+  if (threadIdx.x == 0) s.max_len = g->max_len;
+  __syncthreads();
+}
+
+// One codeword from the next 32 stream bits (left-justified in `window`).
+__device__ __forceinline__ void decode_one(const SmemTables& s, u32 window, u32& sym, u32& len) {
+  const u32 e = s.lut[window >> (32 - kDecLutBits)];
+  len = e & 63u;
+  sym = e >> 6;
+  if (len == 0) {
+    // longer than the LUT window: smallest len with window >= first_code[len] << (32 - len)
+    // (reference include/canonical_huff_encoder.h:157-162 cfind on the left-justified table)
+    len = kDecLutBits + 1;
+    const u32 max_len = s.max_len;
+    while (len < max_len && window < s.first_code_lj[len]) ++len;
+    u32 idx = s.start_pos[len] + ((window - s.first_code_lj[len]) >> (32 - len));
+    idx = idx < u32(GH_NSYM) ? idx : u32(GH_NSYM - 1);
+    sym = s.symbol[idx];
+  }
+}
+
+// ---- MSB-first bit reader over global memory, 128-bit loads --------------------------------------------
+struct BitReader {
+  const uint8_t* bytes;
+  u64 readable;
+  u64 vi;     // index of the 16-byte vector held in `cur`
+  uint4 cur;
+  u32 wpos;   // next 32-bit word of `cur` to hand out
+  u64 buf;    // next `avail` stream bits, left-justified
+  int avail;  // kept >= 32 between symbols
+
+  __device__ __forceinline__ uint4 fetch(u64 v) const {
+    if ((v + 1) * 16 <= readable) return ldg128(reinterpret_cast<const uint4*>(bytes) + v);
+    u32 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      u32 x = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const u64 idx = v * 16 + u64(k * 4 + b);
+        const u32 byte = idx < readable ? u32(bytes[idx]) : 0xffu;  // past the end: the reference's 1-padding
+        x |= byte << (8 * b);
+      }
+      w[k] = x;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ __forceinline__ u32 next_word() {
+    const u32 w = wpos == 0 ? cur.x : wpos == 1 ? cur.y : wpos == 2 ? cur.z : cur.w;
+    if (++wpos == 4) {
+      wpos = 0;
+      ++vi;
+      cur = fetch(vi);
+    }
+    return be32(w);
+  }
+  __device__ __forceinline__ void push() {
+    buf |= u64(next_word()) << (32 - avail);
+    avail += 32;
+  }
+  __device__ __forceinline__ void seek(const uint8_t* base, u64 readable_bytes, u64 bitpos) {
+    bytes = base;
+    readable = readable_bytes;
+    vi = bitpos >> 7;
+    cur = fetch(vi);
+    wpos = u32(bitpos >> 5) & 3u;
+    buf = 0;
+    avail = 0;
+    push();
+    push();
+    const u32 drop = u32(bitpos) & 31u;
+    buf <<= drop;
+    avail -= int(drop);
+  }
+  __device__ __forceinline__ u32 window() const { return u32(buf >> 32); }
+  __device__ __forceinline__ void consume(u32 len) {
+    buf <<= len;
+    avail -= int(len);
+    if (avail < 32) push();
+  }
+};
+
+__device__ __forceinline__ u64 sub_end_bits(const DecGeometry& g, u64 i) {
+  const u64 start = i * u64(g.sub_bytes) * 8;
+  const u64 left = g.slice_bits - start;
+  const u64 full = u64(g.sub_bytes) * 8;
+  return left < full ? left : full;
+}
+
+// ---- K5a: speculative decode of every subsequence from bit 0 (subsequence 0: from the true entry) ---------
+__global__ void __launch_bounds__(kDecThreads)
+dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
+  __shared__ SmemTables s;
+  load_tables(s, ws.tables);
+  const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  if (i >= g.n_sub) return;
+  const u64 start = i * u64(g.sub_bytes) * 8;
+  const u32 end = u32(sub_end_bits(g, i));
+  const u32 entry = (i == 0) ? g.entry0 : 0u;
+  u32 pos = entry, count = 0, eof = 0;
+  BitReader r;
+  r.seek(g.payload, g.readable, start + pos);
+  while (pos < end) {
+    u32 sym, len;
+    decode_one(s, r.window(), sym, len);
+    if (sym == u32(GH_EOF_SYMBOL)) {
+      eof = 1;
+      break;
+    }
+    ++count;
+    pos += len;
+    r.consume(len);
+  }
+  ws.sub[i] = pack_state(count, entry, eof ? 0u : pos - end, eof);
+}
+
+// ---- K5b: one synchronisation round ------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDecThreads)
+dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
+  __shared__ SmemTables s;
+  load_tables(s, ws.tables);
+  const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  if (i >= g.n_sub) return;
+  const u64 mine = ld_volatile_u64(ws.sub + i);
+  const u32 want = (i == 0) ? g.entry0 : st_exit(ld_volatile_u64(ws.sub + i - 1));
+  if (want == st_entry(mine)) return;
+
+  const u64 start = i * u64(g.sub_bytes) * 8;
+  const u32 end = u32(sub_end_bits(g, i));
+  // path A = the stored one (from st_entry(mine)), path B = the one we now believe in (from `want`)
+  u32 pos_a = st_entry(mine), pos_b = want;
+  u32 steps_a = 0, steps_b = 0, eof_b = 0;
+  bool merged = false;
+  BitReader ra, rb;
+  ra.seek(g.payload, g.readable, start + pos_a);
+  rb.seek(g.payload, g.readable, start + pos_b);
+  while (pos_b < end) {
+    if (pos_a == pos_b) {
+      merged = true;
+      break;
+    }
+    u32 sym, len;
+    if (pos_a < pos_b) {  // A is behind (hence still inside the subsequence): advance it
+      decode_one(s, ra.window(), sym, len);
+      if (sym == u32(GH_EOF_SYMBOL)) {
+        pos_a = 0xffffffffu;  // A ended in an end mark: it can never meet B
+      } else {
+        ++steps_a;
+        pos_a += len;
+        ra.consume(len);
+      }
+    } else {
+      decode_one(s, rb.window(), sym, len);
+      if (sym == u32(GH_EOF_SYMBOL)) {
+        eof_b = 1;
+        break;
+      }
+      ++steps_b;
+      pos_b += len;
+      rb.consume(len);
+    }
+  }
+  u32 count, exit, eof;
+  if (merged) {  // from the meeting point on, the stored path is the true one
+    count = steps_b + (st_count(mine) - steps_a);
+    exit = st_exit(mine);
+    eof = st_eof(mine);
+  } else {
+    count = steps_b;
+    eof = eof_b;
+    exit = eof_b ? 0u : pos_b - end;
+  }
+  st_volatile_u64(ws.sub + i, pack_state(count, want, exit, eof));
+  if (exit != st_exit(mine) || eof != st_eof(mine)) ws.ctl->changed = 1u;
+}
+
+// ---- K6: truncate at the first end mark, turn counts into output offsets -----------------------------------
+__global__ void __launch_bounds__(kDecThreads)
+dec_tile_sum_kernel(DecGeometry g, DecWorkspace ws) {
+  __shared__ u32 s_warp[kDecThreads / 32];
+  const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  const u64 st = i < g.n_sub ? ws.sub[i] : 0ull;
+  if (i < g.n_sub && st_eof(st)) atomicMin(&ws.ctl->eof_index, u32(i));
+  const u32 sum = warp_sum(st_count(st));
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u64 total = 0;
+    for (int k = 0; k < kDecThreads / 32; ++k) total += s_warp[k];
+    ws.tile_sum[blockIdx.x] = total;
+  }
+}
+
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
+  __shared__ u64 s_warp[kScanThreads / 32];
+  __shared__ u64 s_partial;
+  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const u64 n_tiles = (g.n_sub + kDecThreads - 1) / kDecThreads;
+  const u32 eof_index = ws.ctl->eof_index;
+  const u64 eof_tile = eof_index == kNoEof ? n_tiles : u64(eof_index) / kDecThreads;
+
+  // the tile holding the end mark only counts subsequences up to and including that one
+  u64 part = 0;
+  if (eof_index != kNoEof && t < unsigned(kDecThreads)) {
+    const u64 i = eof_tile * kDecThreads + t;
+    if (i <= u64(eof_index)) part = st_count(ws.sub[i]);
+  }
+  part = warp_sum64(part);
+  if (lane == 0) s_warp[warp] = part;
+  __syncthreads();
+  if (t == 0) {
+    u64 p = 0;
+    for (int k = 0; k < kScanThreads / 32; ++k) p += s_warp[k];
+    s_partial = p;
+  }
+  __syncthreads();
+  const u64 partial = s_partial;
+
+  u64 carry = 0;
+  for (u64 chunk = 0; chunk < n_tiles; chunk += kScanThreads) {
+    const u64 tile = chunk + t;
+    u64 v = 0;
+    if (tile < n_tiles) v = tile < eof_tile ? ws.tile_sum[tile] : (tile == eof_tile ? partial : 0ull);
+    // block-wide exclusive scan of v
+    u64 incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= unsigned(d)) incl += up;
+    }
+    __syncthreads();  // s_warp reuse
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u64 warp_base = 0, chunk_total = 0;
+    for (int k = 0; k < kScanThreads / 32; ++k) {
+      const u64 wt = s_warp[k];
+      if (unsigned(k) < warp) warp_base += wt;
+      chunk_total += wt;
+    }
+    if (tile < n_tiles) ws.tile_base[tile] = carry + warp_base + incl - v;
+    carry += chunk_total;
+  }
+  if (t == 0) {
+    ws.ctl->total = carry;
+    ws.ctl->eof_found = eof_index != kNoEof;
+    ws.ctl->exit_bit = st_exit(ws.sub[g.n_sub - 1]);
+  }
+}
+
+// ---- K7: final decode from the exact entries, 128-bit stores ---------------------------------------------
+__global__ void __launch_bounds__(kDecThreads)
+dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
+  __shared__ SmemTables s;
+  __shared__ u32 s_warp[kDecThreads / 32];
+  load_tables(s, ws.tables);
+  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const u64 i = u64(blockIdx.x) * kDecThreads + t;
+  const u32 eof_index = ws.ctl->eof_index;
+  u64 st = 0;
+  u32 count = 0;
+  if (i < g.n_sub && i <= u64(eof_index)) {
+    st = ws.sub[i];
+    count = st_count(st);
+  }
+  const u32 incl = warp_inclusive_scan(count, lane);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  u32 warp_base = 0;
+#pragma unroll
+  for (int k = 0; k < kDecThreads / 32; ++k)
+    if (unsigned(k) < warp) warp_base += s_warp[k];
+  const u64 o = ws.tile_base[blockIdx.x] + warp_base + (incl - count);
+  if (count == 0 || o >= out_cap) return;
+  u64 remaining = count;
+  if (remaining > out_cap - o) remaining = out_cap - o;
+
+  BitReader r;
+  r.seek(g.payload, g.readable, i * u64(g.sub_bytes) * 8 + st_entry(st));
+  uint8_t* dst = out + o;
+  u32 sym, len;
+  while (remaining && (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    decode_one(s, r.window(), sym, len);
+    r.consume(len);
+    *dst++ = uint8_t(sym);
+    --remaining;
+  }
+  while (remaining >= 16) {
+    u32 w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      decode_one(s, r.window(), sym, len);
+      r.consume(len);
+      w[k >> 2] |= (sym & 0xffu) << (8 * (k & 3));
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    dst += 16;
+    remaining -= 16;
+  }
+  while (remaining) {
+    decode_one(s, r.window(), sym, len);
+    r.consume(len);
+    *dst++ = uint8_t(sym);
+    --remaining;
+  }
+}
+
+// ---- host orchestration -------------------------------------------------------------------------------
+struct DecLayout {
+  size_t off_tables, off_ctl, off_sub, off_tile_sum, off_tile_base, total;
+};
+
+static DecLayout dec_layout(u64 slice_bytes) {
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const u64 max_sub = slice_bytes / kMinSubBytes + 2;
+  const u64 max_tiles = max_sub / kDecThreads + 2;
+  DecLayout L;
+  L.off_tables = 0;
+  L.off_ctl = up(sizeof(DecodeTables));
+  L.off_sub = L.off_ctl + 256;
+  L.off_tile_sum = L.off_sub + up(size_t(max_sub) * 8);
+  L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
+  L.total = L.off_tile_base + up(size_t(max_tiles) * 8);
+  return L;
+}
+
+static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
+  uint8_t* p = static_cast<uint8_t*>(d_ws);
+  DecWorkspace w;
+  w.tables = reinterpret_cast<const DecodeTables*>(p + L.off_tables);
+  w.ctl = reinterpret_cast<DecControl*>(p + L.off_ctl);
+  w.sub = reinterpret_cast<u64*>(p + L.off_sub);
+  w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
+  w.tile_base = reinterpret_cast<u64*>(p + L.off_tile_base);
+  return w;
+}
+
+static u32 choose_sub_bytes(u64 slice_bytes) {
+  const u64 target = u64(sm_count() > 0 ? sm_count() : 1) * 2048 * 3 / 2;  // ~1.5 resident waves of threads
+  u64 s = (slice_bytes + target - 1) / target;
+  s = (s + kMinSubBytes - 1) / kMinSubBytes * kMinSubBytes;
+  if (s < kMinSubBytes) s = kMinSubBytes;
+  if (s > kMaxSubBytes) s = kMaxSubBytes;
+  return u32(s);
+}
+
+static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream) {
+  const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
+  GH_LAUNCH(dec_tile_sum_kernel, tiles, kDecThreads, 0, stream, g, ws);
+  GH_LAUNCH(dec_offsets_kernel, 1, kScanThreads, 0, stream, g, ws);
+  int rc = check_launch();
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(h_ctl, ws.ctl, sizeof(DecControl), cudaMemcpyDeviceToHost, stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(stream));
+  return GH_OK;
+}
+
+static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 readable, const gh_code* code, u32 entry_bit,
+                            int first_call, gh_shard_sync* result, void* d_ws, size_t ws_bytes, cudaStream_t stream,
+                            DecGeometry* geom_out) {
+  if (!d_payload || !code || !d_ws) return GH_ERR_ARG;
+  if (slice_bytes == 0) return GH_ERR_NO_EOF;
+  if ((reinterpret_cast<uintptr_t>(d_payload) & 15) || (reinterpret_cast<uintptr_t>(d_ws) & 255)) return GH_ERR_ARG;
+  if (readable < slice_bytes || entry_bit > 0xffffu) return GH_ERR_ARG;
+  const DecLayout L = dec_layout(slice_bytes);
+  if (ws_bytes < L.total) return GH_ERR_SPACE;
+  DecWorkspace ws = dec_bind(d_ws, L);
+  DecControl h_ctl;
+  DecGeometry g;
+  g.payload = d_payload;
+  g.slice_bits = slice_bytes * 8;
+  g.readable = readable;
+  g.entry0 = entry_bit;
+
+  if (first_call) {
+    DecodeTables tables;
+    int rc = build_decode_tables(code, &tables);
+    if (rc != GH_OK) return rc;
+    GH_CUDA_TRY(cudaMemcpyAsync(const_cast<DecodeTables*>(ws.tables), &tables, sizeof(tables), cudaMemcpyHostToDevice, stream));
+    g.sub_bytes = choose_sub_bytes(slice_bytes);
+  } else {
+    GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
+    GH_CUDA_TRY(cudaStreamSynchronize(stream));
+    g.sub_bytes = h_ctl.sub_bytes;
+    if (g.sub_bytes < kMinSubBytes || (g.sub_bytes % kMinSubBytes)) return GH_ERR_ARG;
+  }
+
+  u32 total_rounds = 0;
+  bool speculate = first_call != 0;
+  while (true) {
+    g.n_sub = (slice_bytes + g.sub_bytes - 1) / g.sub_bytes;
+    const unsigned blocks = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
+    if (speculate) {
+      GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws);
+      int rc = check_launch();
+      if (rc != GH_OK) return rc;
+    }
+    bool converged = false;
+    const bool can_escalate = g.sub_bytes < kMaxSubBytes && g.n_sub > 1;
+    for (int round = 0; !can_escalate || round < kRoundsBeforeEscalation; ++round) {
+      h_ctl = DecControl();
+      h_ctl.eof_index = kNoEof;
+      h_ctl.sub_bytes = g.sub_bytes;
+      h_ctl.n_sub = g.n_sub;
+      GH_CUDA_TRY(cudaMemcpyAsync(ws.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, stream));
+      GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
+      int rc = check_launch();
+      if (rc != GH_OK) return rc;
+      GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
+      GH_CUDA_TRY(cudaStreamSynchronize(stream));
+      ++total_rounds;
+      if (!h_ctl.changed) {
+        converged = true;
+        break;
+      }
+    }
+    if (converged) break;
+    // slow to synchronise at this granularity: coarser subsequences, start over
+    u64 bigger = u64(g.sub_bytes) * 4;
+    if (bigger > kMaxSubBytes) bigger = kMaxSubBytes;
+    g.sub_bytes = u32(bigger);
+    speculate = true;
+  }
+
+  int rc = dec_finish(g, ws, &h_ctl, stream);
+  if (rc != GH_OK) return rc;
+  if (result) {
+    result->n_symbols = h_ctl.total;
+    result->exit_bit = h_ctl.exit_bit;
+    result->eof_found = h_ctl.eof_found;
+    result->rounds = total_rounds;
+    result->sub_bytes = g.sub_bytes;
+  }
+  if (geom_out) *geom_out = g;
+  return GH_OK;
+}
+
+static int decode_write_impl(const DecGeometry& g, uint8_t* d_out, u64 out_cap, void* d_ws, cudaStream_t stream) {
+  const DecLayout L = dec_layout(g.slice_bits / 8);
+  DecWorkspace ws = dec_bind(d_ws, L);
+  const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
+  GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, 0, stream, g, d_out, out_cap, ws);
+  return check_launch();
+}
+
+}  // namespace gh
+
+extern "C" {
+
+size_t gh_decode_workspace_bytes(uint64_t payload_bytes) { return gh::dec_layout(payload_bytes).total; }
+
+int gh_decode_sync(const uint8_t* d_payload, uint64_t slice_bytes, uint64_t readable_bytes, const gh_code* code,
+                   uint32_t entry_bit, int first_call, gh_shard_sync* result, void* d_workspace,
+                   size_t workspace_bytes, void* stream) {
+  return gh::decode_sync_impl(d_payload, slice_bytes, readable_bytes, code, entry_bit, first_call, result, d_workspace,
+                              workspace_bytes, (cudaStream_t)stream, nullptr);
+}
+
+int gh_decode_write(const uint8_t* d_payload, uint64_t slice_bytes, uint64_t readable_bytes, const gh_code* code,
+                    uint8_t* d_out, uint64_t out_cap, void* d_workspace, size_t workspace_bytes, void* stream) {
+  using namespace gh;
+  (void)code;
+  if (!d_payload || !d_workspace || (!d_out && out_cap)) return GH_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(d_payload) & 15) || (reinterpret_cast<uintptr_t>(d_workspace) & 255)) return GH_ERR_ARG;
+  const DecLayout L = dec_layout(slice_bytes);
+  if (workspace_bytes < L.total) return GH_ERR_SPACE;
+  DecWorkspace ws = dec_bind(d_workspace, L);
+  DecControl h_ctl;
+  GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GH_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  DecGeometry g;
+  g.payload = d_payload;
+  g.slice_bits = slice_bytes * 8;
+  g.readable = readable_bytes;
+  g.sub_bytes = h_ctl.sub_bytes;
+  g.n_sub = h_ctl.n_sub;
+  g.entry0 = 0;
+  if (g.sub_bytes < kMinSubBytes || g.n_sub != (slice_bytes + g.sub_bytes - 1) / g.sub_bytes) return GH_ERR_ARG;
+  return decode_write_impl(g, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+}
+
+int gh_decode(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code* code, uint8_t* d_out,
+              uint64_t out_cap, uint64_t* n_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+  return gh::decode_full(d_payload, payload_bytes, code, 0, d_out, out_cap, n_out, d_workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace gh {
+
+int decode_full(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code* code, uint32_t entry_bit,
+                uint8_t* d_out, uint64_t out_cap, uint64_t* n_out, void* d_workspace, size_t workspace_bytes,
+                void* stream) {
+  gh_shard_sync res;
+  DecGeometry g;
+  int rc = decode_sync_impl(d_payload, payload_bytes, payload_bytes, code, entry_bit, 1, &res, d_workspace,
+                            workspace_bytes, (cudaStream_t)stream, &g);
+  if (rc != GH_OK) return rc;
+  if (n_out) *n_out = res.n_symbols;
+  if (!d_out && out_cap) return GH_ERR_ARG;
+  rc = decode_write_impl(g, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (!res.eof_found) return GH_ERR_NO_EOF;
+  if (res.n_symbols > out_cap) return GH_ERR_SPACE;
+  return GH_OK;
+}
+
+}  // namespace gh

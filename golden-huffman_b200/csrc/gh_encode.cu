@@ -1,0 +1,287 @@
+// K2-K4 -- LUT gather, device-wide bit-offset scan and bit packing in ONE pass over the input
+// (replaces reference include/canonical_huff_encoder.cc:245-285 encode_file/encode_each_byte and the
+// per-bit writer utils/include/buffer.h:241-248,277-295).
+//
+// Algorithmic traffic: N bytes read + C bytes written (the scan is fused by decoupled look-back, so the
+// input is not read a second time to learn the bit offsets).
+//
+// A tile is kEncThreads x 16 input bytes. Per tile:
+//   1. every thread loads one 128-bit vector (coalesced) and gathers (codeword, length) for its 16 bytes
+//      from the shared-memory LUT, keeping them in registers;
+//   2. the per-thread bit counts are scanned across the block (warp shuffles), the tile total is published
+//      and the tile's global bit offset G is obtained by a warp-wide decoupled look-back over the
+//      predecessors' (flag | value) words;
+//   3. each thread shifts its codewords into a 64-bit MSB-first accumulator and drops finished 32-bit
+//      words into a shared staging buffer whose word 0 is global word G/32 (so the tile is already
+//      phase-aligned with the output);
+//   4. the staged words are byte-swapped to stream order and stored coalesced. The tile's first word, when
+//      it is shared with the previous tile, is NOT stored: its bits go to head[tile] and a tiny second
+//      kernel ORs them into the word the previous tile wrote -- every output word has exactly one writer
+//      per kernel, no global atomics on the payload.
+// The thread that owns the last input byte also appends the end-of-encoding codeword and the 1-padding
+// (reference include/canonical_huff_encoder.cc:255-257).
+#include "gh_common.cuh"
+
+namespace gh {
+
+constexpr int kEncThreads = 256;
+constexpr int kEncBytesPerThread = 16;
+constexpr int kEncTileBytes = kEncThreads * kEncBytesPerThread;
+// worst case per tile: 4096 symbols x 32 bits + end mark 32 + padding 7 + phase 31
+constexpr int kEncStageWords = (kEncTileBytes * 32 + 32 + 7 + 31 + 31) / 32 + 1;
+
+constexpr u64 kFlagMask = 3ull << 62;
+constexpr u64 kFlagAggregate = 1ull << 62;  // value = bits of this tile only
+constexpr u64 kFlagPrefix = 2ull << 62;     // value = global bit offset just after this tile
+
+struct EncWorkspace {
+  u64* tile_state;  // [ntiles]
+  u32* head;        // [ntiles]
+  u32* ticket;      // tile dispenser (tiles are handed out in the order blocks become resident)
+};
+
+__host__ __device__ inline u64 enc_num_tiles(u64 n) { return (n + kEncTileBytes - 1) / kEncTileBytes; }
+
+__global__ void __launch_bounds__(kEncThreads)
+encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
+              u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
+  __shared__ u32 s_code[GH_NSYM + 3];
+  __shared__ uint8_t s_len[GH_NSYM + 3];
+  __shared__ u32 s_stage[kEncStageWords];
+  __shared__ u32 s_warp_total[kEncThreads / 32];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_tile_start;
+
+  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);
+  for (unsigned s = t; s < GH_NSYM; s += kEncThreads) {
+    s_code[s] = table.codeword[s];
+    s_len[s] = table.length[s];
+  }
+  __syncthreads();
+  const u64 tile = s_tile;
+  const u64 ntiles = enc_num_tiles(n);
+  const bool last_tile = (tile + 1 == ntiles);
+
+  // ---- 1. load + gather --------------------------------------------------------------------------
+  const u64 base = tile * kEncTileBytes + u64(t) * kEncBytesPerThread;
+  u32 w[4] = {0, 0, 0, 0};
+  int cnt = 0;
+  if (base + kEncBytesPerThread <= n) {
+    const uint4 v = ldg128(reinterpret_cast<const uint4*>(in + base));
+    w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+    cnt = kEncBytesPerThread;
+  } else if (base < n) {
+    cnt = int(n - base);
+    for (int k = 0; k < cnt; ++k) w[k >> 2] |= u32(in[base + k]) << (8 * (k & 3));
+  }
+  u32 code[kEncBytesPerThread];
+  u32 len[kEncBytesPerThread];
+  u32 my_bits = 0;
+#pragma unroll
+  for (int k = 0; k < kEncBytesPerThread; ++k) {
+    const u32 b = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+    const bool live = k < cnt;
+    code[k] = s_code[b];
+    len[k] = live ? u32(s_len[b]) : 0u;
+    my_bits += len[k];
+  }
+  // the owner of the last byte also carries the end mark (its padding is only known after the scan)
+  const bool owns_end = append_eof && last_tile && (base < n) && (base + kEncBytesPerThread >= n);
+  const u32 eof_code = s_code[GH_EOF_SYMBOL];
+  const u32 eof_len = owns_end ? u32(s_len[GH_EOF_SYMBOL]) : 0u;
+  my_bits += eof_len;
+
+  // ---- 2. block scan + decoupled look-back -----------------------------------------------------------
+  const u32 incl = warp_inclusive_scan(my_bits, lane);
+  if (lane == 31) s_warp_total[warp] = incl;
+  __syncthreads();
+  u32 warp_base = 0, tile_bits = 0;
+#pragma unroll
+  for (int k = 0; k < kEncThreads / 32; ++k) {
+    const u32 wt = s_warp_total[k];
+    if (unsigned(k) < warp) warp_base += wt;
+    tile_bits += wt;
+  }
+  const u32 excl = warp_base + incl - my_bits;  // bits of this tile before this thread
+
+  if (warp == 0) {
+    u64 exclusive = start_bit;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(ws.tile_state, kFlagPrefix | (start_bit + tile_bits));
+    } else {
+      if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
+      exclusive = 0;
+      long long look = (long long)tile - 1;
+      while (true) {
+        const long long idx = look - (long long)lane;
+        u64 st = kFlagPrefix;  // virtual tiles before tile 0 contribute nothing
+        if (idx >= 0) {
+          do {
+            st = ld_volatile_u64(ws.tile_state + idx);
+          } while ((st & kFlagMask) == 0);
+        }
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
+        // lanes up to and including the nearest tile that already knows its prefix contribute
+        const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;  // has_prefix != 0 once idx < 0 is reached
+        u64 contrib = (has_prefix == 0 || lane <= first) ? (st & ~kFlagMask) : 0ull;
+        exclusive += warp_sum64(contrib);
+        if (has_prefix) break;
+        look -= 32;
+      }
+      if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
+    }
+    if (lane == 0) s_tile_start = exclusive;
+  }
+
+  // ---- 3. pack into the phase-aligned staging buffer ----------------------------------------------
+  // zero the words this tile can touch (tile_bits + padding + phase)
+  const u32 zero_words = (tile_bits + 31 + 7 + 31) / 32 + 1;
+  for (u32 i = t; i < zero_words && i < u32(kEncStageWords); i += kEncThreads) s_stage[i] = 0;
+  __syncthreads();
+  const u64 G = s_tile_start;
+  const u32 phase = u32(G & 31);
+  const u64 my_start = u64(phase) + excl;  // bit position inside the staging buffer
+  u32 wi = u32(my_start >> 5);
+  u32 fill = u32(my_start & 31);  // bits of word wi that belong to earlier threads (kept zero here)
+  u64 acc = 0;                    // bits [63 .. 64-fill) stay zero, ours follow
+  bool first_word = true;
+
+  auto put = [&](u32 c, u32 l) {
+    // l in 0..32, fill in 0..31 -> fill + l <= 63
+    if (l) acc |= u64(c) << (64 - fill - l);
+    fill += l;
+    if (fill >= 32) {
+      const u32 word = u32(acc >> 32);
+      if (first_word) {
+        atomicOr(&s_stage[wi], word);  // may share the word with the previous thread's tail
+        first_word = false;
+      } else {
+        s_stage[wi] = word;  // a word this thread filled from bit 31 down: exclusively ours
+      }
+      ++wi;
+      acc <<= 32;
+      fill -= 32;
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < kEncBytesPerThread; ++k) put(code[k], len[k]);
+  u64 tile_bits_padded = tile_bits;
+  if (owns_end) {
+    put(eof_code, eof_len);
+    const u64 end_bit = G + excl + my_bits;  // first bit after the end mark
+    const u32 pad = u32((8 - (end_bit & 7)) & 7);
+    put((1u << pad) - 1u, pad);  // flush_bits(): fill the last byte with 1s (utils/include/buffer.h:277-280)
+    if (end_bit_out) *end_bit_out = end_bit;
+  }
+  if (fill) atomicOr(&s_stage[wi], u32(acc >> 32));
+  if (!append_eof && last_tile && t == 0 && end_bit_out) *end_bit_out = G + tile_bits;
+  if (append_eof && last_tile) {
+    const u64 end_bit = G + tile_bits;
+    tile_bits_padded += (8 - (end_bit & 7)) & 7;
+  }
+  __syncthreads();
+
+  // ---- 4. store: one writer per output word ------------------------------------------------------------
+  const u64 word0 = G >> 5;
+  const u32 nwords = u32((u64(phase) + tile_bits_padded + 31) >> 5);
+  const bool shared_head = (tile > 0) && (phase != 0);
+  if (shared_head && t == 0) ws.head[tile] = s_stage[0];
+  for (u32 i = t + (shared_head ? 1u : 0u); i < nwords; i += kEncThreads) {
+    const u64 gw = word0 + i;
+    if (gw < out_word_cap) out_words[gw] = be32(s_stage[i]);
+  }
+}
+
+// Second kernel: OR each tile's deferred head bits into the word its predecessor stored.
+// Thread = tile. The first tile (in order) holding head bits for a given word merges the whole run.
+__global__ void __launch_bounds__(256)
+encode_stitch_kernel(u64 ntiles, u64 start_bit, u32* __restrict__ out_words, u64 out_word_cap, EncWorkspace ws) {
+  const u64 tile = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tile == 0 || tile >= ntiles) return;
+  const u64 g = ws.tile_state[tile - 1] & ~kFlagMask;  // global start bit of `tile`
+  if ((g & 31) == 0) return;                            // starts on a word boundary: nothing deferred
+  const u64 word = g >> 5;
+  if (tile >= 2) {
+    const u64 gp = ws.tile_state[tile - 2] & ~kFlagMask;  // start of the previous tile
+    if ((gp >> 5) == word && (gp & 31) != 0) return;       // the previous tile deferred into this word too: it leads
+  }
+  (void)start_bit;
+  u32 bits = ws.head[tile];
+  for (u64 nx = tile + 1; nx < ntiles; ++nx) {  // only ever iterates for degenerate sub-word tiles
+    const u64 gn = ws.tile_state[nx - 1] & ~kFlagMask;
+    if ((gn >> 5) != word) break;
+    bits |= ws.head[nx];
+  }
+  if (word < out_word_cap) out_words[word] |= be32(bits);
+}
+
+inline size_t enc_ws_bytes(u64 n) {
+  const u64 nt = enc_num_tiles(n) + 1;
+  return size_t(nt * 8 + ((nt * 4 + 7) / 8) * 8 + 256);
+}
+
+}  // namespace gh
+
+extern "C" {
+
+size_t gh_encode_workspace_bytes(uint64_t n) { return gh::enc_ws_bytes(n); }
+
+uint64_t gh_encode_payload_capacity(uint64_t n, const gh_code* code, uint64_t start_bit) {
+  const uint64_t max_len = code ? code->max_len : 32;
+  const uint64_t bits = start_bit + n * max_len + 32 + 7;
+  return ((bits + 127) / 128) * 16 + 16;
+}
+
+int gh_encode(const uint8_t* d_in, uint64_t n, const gh_code* code, uint64_t start_bit, int append_eof,
+              uint8_t* d_payload, uint64_t payload_cap, uint64_t* d_end_bit, void* d_workspace,
+              size_t workspace_bytes, void* stream) {
+  if (code && payload_cap < gh_encode_payload_capacity(n, code, start_bit)) return GH_ERR_SPACE;
+  return gh::encode_unchecked(d_in, n, code, start_bit, append_eof, d_payload, payload_cap, d_end_bit, d_workspace,
+                              workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace gh {
+
+int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint64_t start_bit, int append_eof,
+                     uint8_t* d_payload, uint64_t payload_cap, uint64_t* d_end_bit, void* d_workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!code || !d_payload || !d_workspace) return GH_ERR_ARG;
+  if (n == 0) return GH_ERR_EMPTY;
+  if (!d_in) return GH_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_payload) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_workspace) & 7))
+    return GH_ERR_ARG;
+  if (workspace_bytes < enc_ws_bytes(n)) return GH_ERR_SPACE;
+  EncodeTable table;
+  int rc = build_encode_table(code, &table);
+  if (rc != GH_OK) return rc;
+  const u64 ntiles = enc_num_tiles(n);
+  if (ntiles > 0x7fffffffull) return GH_ERR_ARG;
+
+  EncWorkspace ws;
+  uint8_t* p = static_cast<uint8_t*>(d_workspace);
+  ws.tile_state = reinterpret_cast<u64*>(p);
+  p += (ntiles + 1) * 8;
+  ws.head = reinterpret_cast<u32*>(p);
+  p += (((ntiles + 1) * 4 + 7) / 8) * 8;
+  ws.ticket = reinterpret_cast<u32*>(p);
+  const size_t used = size_t(p - static_cast<uint8_t*>(d_workspace)) + 8;
+  GH_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, used, (cudaStream_t)stream));
+
+  const u64 out_word_cap = payload_cap / 4;
+  GH_LAUNCH(encode_kernel, unsigned(ntiles), kEncThreads, 0, stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
+            reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
+  rc = check_launch();
+  if (rc != GH_OK) return rc;
+  if (ntiles > 1) {
+    GH_LAUNCH(encode_stitch_kernel, unsigned((ntiles + 255) / 256), 256, 0, stream, ntiles, (u64)start_bit,
+              reinterpret_cast<u32*>(d_payload), out_word_cap, ws);
+    rc = check_launch();
+  }
+  return rc;
+}
+
+}  // namespace gh

@@ -1,0 +1,152 @@
+"""Kernel logic on the CPU: the product's .cu sources compiled against tests/emul/cuda_emul.h (threads of a
+block = OS threads, blocks run one after another) and compared bit-for-bit with the oracle. This checks
+indexing, barriers, the look-back bookkeeping, bit packing and the self-synchronising decode before any GPU
+time is spent; real concurrency is only exercised by the -m gpu tests."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import emul_lib
+from emul_lib import aligned
+from golden_cases import make_input
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return emul_lib.load()
+
+
+@pytest.fixture(scope="module")
+def ctx(emu):
+    c = emu.ctx_create()
+    yield c
+    emu.ctx_destroy(c)
+
+
+def _roundtrip(emu, ctx, oracle, data):
+    n = len(data)
+    d = np.frombuffer(data, dtype=np.uint8)
+    din = aligned(n + 16)
+    din[:n] = d
+    hist = aligned(256, np.uint64)
+    emu.histogram(din.ctypes.data, n, hist.ctypes.data)
+    assert (hist == oracle.histogram(data)).all()
+    rc, img = oracle.compress(data)
+    assert rc == 0
+    cap = emu.compress_bound(n)
+    dout = aligned(cap)
+    nb, _ = emu.compress_device(ctx, din.ctypes.data, n, dout.ctypes.data, cap)
+    assert dout[:nb].tobytes() == img
+    dimg = aligned(nb + 32)
+    dimg[:nb] = np.frombuffer(img, dtype=np.uint8)
+    dde = aligned(n + 64)
+    nd, _ = emu.decompress_device(ctx, dimg.ctypes.data, nb, dde.ctypes.data, n + 64)
+    assert nd == n and dde[:n].tobytes() == data
+    return img
+
+
+@pytest.mark.parametrize("name", ["kat1_abracadabra", "kat2_a1000", "one_byte", "two_symbols", "text_small",
+                                  "tile_exact_4096", "tile_plus1_4097"])
+def test_emulated_kernels_on_golden(emu, ctx, oracle, name):
+    _roundtrip(emu, ctx, oracle, make_input(name))
+
+
+def test_emulated_kernels_random(emu, ctx, oracle):
+    rng = np.random.default_rng(3)
+    sizes = [3, 17, 4095, 8193, 30000]
+    for i, n in enumerate(sizes):
+        if i % 3 == 0:
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif i % 3 == 1:
+            d = np.minimum(rng.geometric(0.25, n), 255).astype(np.uint8)
+        else:
+            d = rng.integers(0, 3, n, dtype=np.uint8)
+        _roundtrip(emu, ctx, oracle, d.tobytes())
+
+
+def test_emulated_long_codes(emu, ctx, oracle):
+    """Fibonacci counts -> code lengths up to 21 here: exercises the beyond-LUT search and 64-bit packing"""
+    f = [1, 2]
+    while len(f) < 21:
+        f.append(f[-1] + f[-2])
+    data = np.concatenate([np.full(c, i * 7 % 256, dtype=np.uint8) for i, c in enumerate(f)])
+    np.random.default_rng(5).shuffle(data)
+    img = _roundtrip(emu, ctx, oracle, data.tobytes())
+    _, code = oracle.parse_header(img)
+    assert code.max_len >= 20
+
+
+def test_emulated_encode_start_bit_and_no_eof(emu, oracle):
+    """sharding contract of gh_encode: phase-aligned slice, zero bits before start_bit, no end mark"""
+    data = make_input("text_small")
+    n = len(data)
+    rc, code = oracle.build_code(oracle.histogram(data))
+    _, full = oracle.encode_payload(data, code)
+    bits = np.unpackbits(np.frombuffer(full, dtype=np.uint8))
+    total = oracle.payload_bits(code, oracle.histogram(data)) - code.length[256]
+    import golden_huffman_b200 as gh
+    pcode = gh.GhCode.from_buffer_copy(bytes(code))
+    for start_bit in (0, 5, 31, 32, 77, 127):
+        din = aligned(n + 16)
+        din[:n] = np.frombuffer(data, dtype=np.uint8)
+        cap = emu.encode_payload_capacity(n, pcode, start_bit)
+        out = aligned(cap)
+        out[:] = 0xAA
+        ws = aligned(emu.encode_workspace_bytes(n) + 256)
+        end = aligned(1, np.uint64)
+        emu.encode(din.ctypes.data, n, pcode, out.ctypes.data, cap, ws.ctypes.data, ws.size, start_bit=start_bit,
+                   append_eof=False, d_end_bit=end.ctypes.data)
+        assert int(end[0]) == start_bit + total
+        first_word = start_bit // 32 * 4
+        assert (out[:first_word] == 0xAA).all()  # untouched before the first word
+        got = np.unpackbits(out[first_word:])
+        lead = start_bit - first_word * 8
+        assert not got[:lead].any()
+        assert (got[lead:lead + total] == bits[:total]).all()
+
+
+def test_emulated_sharded_decode_sync(emu, oracle):
+    """the two halves of gh_decode on a payload cut in two: slice 1 first assumes entry 0, then is corrected
+    with slice 0's exit_bit; concatenated output equals the input"""
+    import golden_huffman_b200 as gh
+    data = make_input("text_small") * 3
+    rc, code = oracle.build_code(oracle.histogram(data))
+    _, payload = oracle.encode_payload(data, code)
+    pcode = gh.GhCode.from_buffer_copy(bytes(code))
+    cut = (len(payload) // 2) // 16 * 16
+    buf = aligned(len(payload) + 16)
+    buf[:len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+    slices = [(0, cut, min(cut + 8, len(payload))), (cut, len(payload) - cut, len(payload) - cut)]
+    ws = [aligned(emu.decode_workspace_bytes(s[1]) + 256) for s in slices]
+    res = []
+    for k, (off, nb, readable) in enumerate(slices):
+        res.append(emu.decode_sync(buf.ctypes.data + off, nb, readable, pcode, 0, True, ws[k].ctypes.data, ws[k].size))
+    assert not res[0].eof_found
+    res[1] = emu.decode_sync(buf.ctypes.data + cut, slices[1][1], slices[1][2], pcode, res[0].exit_bit, False,
+                             ws[1].ctypes.data, ws[1].size)
+    assert res[1].eof_found and res[0].n_symbols + res[1].n_symbols == len(data)
+    out = aligned(len(data) + 16)
+    o = 0
+    for k, (off, nb, readable) in enumerate(slices):
+        emu.decode_write(buf.ctypes.data + off, nb, readable, pcode, out.ctypes.data + o, res[k].n_symbols,
+                         ws[k].ctypes.data, ws[k].size)
+        o += res[k].n_symbols
+    assert out[:len(data)].tobytes() == data
+
+
+def test_emulated_decode_errors(emu, ctx, oracle):
+    import golden_huffman_b200 as gh
+    data = make_input("text_small")
+    rc, img = oracle.compress(data)
+    n = len(data)
+    dimg = aligned(len(img) + 32)
+    dimg[:len(img)] = np.frombuffer(img, dtype=np.uint8)
+    out = aligned(n + 64)
+    # output too small: the count is still reported
+    nd, rc = emu.decompress_device(ctx, dimg.ctypes.data, len(img), out.ctypes.data, n - 10, allow=(gh.capi.GH_ERR_SPACE,))
+    assert rc == gh.capi.GH_ERR_SPACE and nd == n
+    # truncated stream: no end mark
+    nd, rc = emu.decompress_device(ctx, dimg.ctypes.data, len(img) - 40, out.ctypes.data, n + 64,
+                                   allow=(gh.capi.GH_ERR_NO_EOF,))
+    assert rc == gh.capi.GH_ERR_NO_EOF

@@ -238,7 +238,10 @@ def main():
     for _ in range(max(args.warmup, 3)):
         _, enc_res, out, nsym = step()
     torch.cuda.synchronize()
-    assert nsym == n and torch.equal(out[:n], x), "round trip mismatch"
+    if world > 1:
+        assert sc.verify_roundtrip(x, out, nsym), "sharded round trip mismatch"
+    else:
+        assert nsym == n and torch.equal(out[:n], x), "round trip mismatch"
     comp_bytes = int(enc_res) if world == 1 else int(enc_res["payload_bytes"])
 
     sampler = ClockSampler(local_rank)

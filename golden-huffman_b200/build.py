@@ -55,6 +55,14 @@ def build(force=False, verbose=False):
             subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
                             "-I" + HOST, "-o", CLI, cli_src, "-L" + LIBDIR, "-lgh_b200",
                             "-Wl,-rpath,$ORIGIN"], check=True)
+        # the same CLI compiled against the reference's UNMODIFIED compressor.h (build container only): the
+        # binary travels to the GPU box, where tests/test_gpu_cli.py runs it
+        ref_inc = "/root/reference/include"
+        if os.path.exists(os.path.join(ref_inc, "compressor.h")):
+            cxx = shutil.which("g++") or "g++"
+            subprocess.run([cxx, "-O2", "-std=c++17", "-w", "-DGH_USE_REFERENCE_FRAME", "-I" + ref_inc,
+                            "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-o", CLI + "_refframe", cli_src,
+                            "-L" + LIBDIR, "-lgh_b200", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

@@ -73,6 +73,10 @@ SIGNATURES = {
     "gh_decompress_host": (_INT, [_VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
     "gh_compress_device": (_INT, [_VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
     "gh_decompress_device": (_INT, [_VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
+    "gh_stage_input": (_INT, [_VP, _VP, _U64, _VP]),
+    "gh_encode_staged": (_INT, [_VP, _CODEP, _VP, _U64, C.POINTER(_U64)]),
+    "gh_stage_payload": (_INT, [_VP, _VP, _U64, _CODEP, C.POINTER(_U64)]),
+    "gh_decode_staged": (_INT, [_VP, _VP, _U64]),
 }
 
 

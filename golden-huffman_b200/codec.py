@@ -12,10 +12,6 @@ import torch
 from .capi import GhLib, GH_ERR_SPACE
 
 
-def _stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
-
-
 class Codec:
     def __init__(self, lib=None, device=None):
         if not torch.cuda.is_available():
@@ -25,6 +21,13 @@ class Codec:
         with torch.cuda.device(self.device):
             self.ctx = self.lib.ctx_create()
         self._ws = None
+
+    def _stream(self):
+        """raw cudaStream_t of torch's current stream: kernels are launched where torch would launch them"""
+        return torch.cuda.current_stream().cuda_stream
+
+    def _sync(self):
+        torch.cuda.current_stream().synchronize()
 
     def close(self):
         if self.ctx:
@@ -43,16 +46,16 @@ class Codec:
             self._ws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    @staticmethod
-    def _check_u8(x):
-        assert x.dtype == torch.uint8 and x.is_cuda and x.is_contiguous(), "expected a contiguous CUDA uint8 tensor"
+    def _check_u8(self, x):
+        assert x.dtype == torch.uint8 and x.device == self.device and x.is_contiguous(), \
+            "expected a contiguous uint8 tensor on the codec's device"
 
     # ---- the path, step by step -------------------------------------------------------------------------
     def histogram(self, x, out=None, accumulate=False):
         """K1: 256 byte counts (torch.int64 tensor on the device)."""
         self._check_u8(x)
         hist = out if out is not None else torch.empty(256, dtype=torch.int64, device=x.device)
-        self.lib.histogram(x.data_ptr(), x.numel(), hist.data_ptr(), accumulate, _stream_ptr())
+        self.lib.histogram(x.data_ptr(), x.numel(), hist.data_ptr(), accumulate, self._stream())
         return hist
 
     def build_code(self, hist):
@@ -71,7 +74,7 @@ class Codec:
         ws = self._workspace(ws_bytes)
         end_bit = torch.zeros(1, dtype=torch.int64, device=x.device)
         self.lib.encode(x.data_ptr(), n, code, payload.data_ptr(), payload.numel(), ws.data_ptr(), ws.numel(),
-                        start_bit=start_bit, append_eof=append_eof, d_end_bit=end_bit.data_ptr(), stream=_stream_ptr())
+                        start_bit=start_bit, append_eof=append_eof, d_end_bit=end_bit.data_ptr(), stream=self._stream())
         return payload, end_bit
 
     def decode(self, payload, nbytes, code, out_cap, out=None, allow=()):
@@ -81,7 +84,7 @@ class Codec:
         ws_bytes = self.lib.decode_workspace_bytes(nbytes)
         ws = self._workspace(ws_bytes)
         n, rc = self.lib.decode(payload.data_ptr(), nbytes, code, dst.data_ptr(), out_cap, ws.data_ptr(), ws.numel(),
-                                _stream_ptr(), allow=allow)
+                                self._stream(), allow=allow)
         return dst, n, rc
 
     # ---- whole .crs2 images -----------------------------------------------------------------------------
@@ -90,14 +93,14 @@ class Codec:
         self._check_u8(x)
         cap = self.lib.compress_bound(x.numel()) if out is None else out.numel()
         img = out if out is not None else torch.empty(cap, dtype=torch.uint8, device=x.device)
-        torch.cuda.current_stream().synchronize()  # the context runs on its own stream
+        self._sync()  # the context runs on its own stream
         nbytes, _ = self.lib.compress_device(self.ctx, x.data_ptr(), x.numel(), img.data_ptr(), cap)
         return img[:nbytes]
 
     def decompress(self, img, out_cap, out=None, allow=()):
         self._check_u8(img)
         dst = out if out is not None else torch.empty(max(out_cap, 1), dtype=torch.uint8, device=img.device)
-        torch.cuda.current_stream().synchronize()
+        self._sync()
         n, rc = self.lib.decompress_device(self.ctx, img.data_ptr(), img.numel(), dst.data_ptr(), out_cap, allow=allow)
         return dst[: min(n, out_cap)], n, rc
 

@@ -16,6 +16,11 @@ struct gh_ctx {
   size_t ws_cap;
   uint64_t* d_small;  // 256 histogram counters + end bit
   uint8_t* h_small;   // pinned: histogram read-back, header staging
+  // state of the staged (step-by-step) entry points
+  uint64_t staged_n;         // input bytes resident in d_in (gh_stage_input)
+  uint64_t staged_payload;   // payload bytes resident in d_in (gh_stage_payload)
+  uint64_t staged_symbols;   // symbols gh_stage_payload found
+  gh_code staged_code;
 };
 
 namespace gh {
@@ -175,6 +180,87 @@ int gh_decompress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, u
   *out_bytes = bytes;
   if (rc != GH_OK) return rc;
   GH_CUDA_TRY(cudaMemcpyAsync(out, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GH_OK;
+}
+
+
+int gh_stage_input(gh_ctx* c, const uint8_t* in, uint64_t n, uint64_t hist256[256]) {
+  using namespace gh;
+  if (!c || !hist256) return GH_ERR_ARG;
+  if (n == 0) return GH_ERR_EMPTY;
+  if (!in) return GH_ERR_ARG;
+  c->staged_n = 0;
+  int rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, n + 16);
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+  rc = gh_histogram(c->d_in, n, c->d_small, 0, c->stream);
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(c->h_small, c->d_small, 256 * 8, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(hist256, c->h_small, 256 * 8);
+  c->staged_n = n;
+  return GH_OK;
+}
+
+int gh_encode_staged(gh_ctx* c, const gh_code* code, uint8_t* out_payload, uint64_t cap, uint64_t* payload_bytes) {
+  using namespace gh;
+  if (!c || !code || !out_payload || !payload_bytes) return GH_ERR_ARG;
+  if (c->staged_n == 0) return GH_ERR_ARG;  // gh_stage_input must come first
+  const uint64_t n = c->staged_n;
+  const uint64_t dev_cap = gh_encode_payload_capacity(n, code, 0);
+  int rc = grow(reinterpret_cast<void**>(&c->d_out), &c->out_cap, dev_cap);
+  if (rc != GH_OK) return rc;
+  rc = grow(&c->d_ws, &c->ws_cap, gh_encode_workspace_bytes(n));
+  if (rc != GH_OK) return rc;
+  uint64_t* d_end = c->d_small + 256;
+  rc = gh_encode(c->d_in, n, code, 0, 1, c->d_out, c->out_cap, d_end, c->d_ws, c->ws_cap, c->stream);
+  if (rc != GH_OK) return rc;
+  uint64_t* h_end = reinterpret_cast<uint64_t*>(c->h_small);
+  GH_CUDA_TRY(cudaMemcpyAsync(h_end, d_end, 8, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const uint64_t bytes = (*h_end + 7) / 8;
+  *payload_bytes = bytes;
+  if (bytes > cap) return GH_ERR_SPACE;
+  GH_CUDA_TRY(cudaMemcpyAsync(out_payload, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return GH_OK;
+}
+
+int gh_stage_payload(gh_ctx* c, const uint8_t* payload, uint64_t nbytes, const gh_code* code, uint64_t* n_symbols) {
+  using namespace gh;
+  if (!c || !payload || !code || !n_symbols) return GH_ERR_ARG;
+  if (nbytes == 0) return GH_ERR_NO_EOF;
+  c->staged_payload = 0;
+  c->staged_n = 0;
+  int rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, nbytes + 16);
+  if (rc != GH_OK) return rc;
+  GH_CUDA_TRY(cudaMemcpyAsync(c->d_in, payload, nbytes, cudaMemcpyHostToDevice, c->stream));
+  rc = grow(&c->d_ws, &c->ws_cap, gh_decode_workspace_bytes(nbytes) + 256);
+  if (rc != GH_OK) return rc;
+  gh_shard_sync res;
+  rc = gh_decode_sync(c->d_in, nbytes, nbytes, code, 0, 1, &res, c->d_ws, c->ws_cap, c->stream);
+  if (rc != GH_OK) return rc;
+  *n_symbols = res.n_symbols;
+  if (!res.eof_found) return GH_ERR_NO_EOF;
+  c->staged_payload = nbytes;
+  c->staged_symbols = res.n_symbols;
+  c->staged_code = *code;
+  return GH_OK;
+}
+
+int gh_decode_staged(gh_ctx* c, uint8_t* out, uint64_t cap) {
+  using namespace gh;
+  if (!c || (!out && cap)) return GH_ERR_ARG;
+  if (c->staged_payload == 0) return GH_ERR_ARG;  // gh_stage_payload must come first
+  const uint64_t n = c->staged_symbols;
+  if (cap < n) return GH_ERR_SPACE;
+  int rc = grow(reinterpret_cast<void**>(&c->d_out), &c->out_cap, n + 16);
+  if (rc != GH_OK) return rc;
+  rc = gh_decode_write(c->d_in, c->staged_payload, c->staged_payload, &c->staged_code, c->d_out, n, c->d_ws, c->ws_cap,
+                       c->stream);
+  if (rc != GH_OK) return rc;
+  if (n) GH_CUDA_TRY(cudaMemcpyAsync(out, c->d_out, n, cudaMemcpyDeviceToHost, c->stream));
   GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return GH_OK;
 }

@@ -167,6 +167,21 @@ int gh_compress_device(gh_ctx* ctx, const uint8_t* d_in, uint64_t n, uint8_t* d_
 int gh_decompress_device(gh_ctx* ctx, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
                          uint64_t* out_bytes);
 
+/* ------------------------------------------------------------------------------------------------
+ * Staged variants, one per step of the reference's template methods, for adapters that must keep the
+ * reference's call order (Compressor::compress: caculate_frequency -> gen_encode -> write_encode_info ->
+ * encode_file; Decompressor::decompress: get_encode_info -> decode_file). Device buffers live in the ctx
+ * between the calls. All synchronous.
+ * ---------------------------------------------------------------------------------------------- */
+/* caculate_frequency(): H2D copy of the whole input + K1; the 256 counters come back to the host */
+int gh_stage_input(gh_ctx* ctx, const uint8_t* in, uint64_t n, uint64_t hist256[256]);
+/* encode_file(): K2-K4 over the staged input, then D2H of the payload (ceil(bits/8) bytes) */
+int gh_encode_staged(gh_ctx* ctx, const gh_code* code, uint8_t* out_payload, uint64_t cap, uint64_t* payload_bytes);
+/* decode_file(), first half: H2D of the payload + K5/K6; reports how many symbols precede the end mark */
+int gh_stage_payload(gh_ctx* ctx, const uint8_t* payload, uint64_t nbytes, const gh_code* code, uint64_t* n_symbols);
+/* decode_file(), second half: K7 + D2H of the n_symbols bytes reported by gh_stage_payload */
+int gh_decode_staged(gh_ctx* ctx, uint8_t* out, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,3 +150,28 @@ def test_emulated_decode_errors(emu, ctx, oracle):
     nd, rc = emu.decompress_device(ctx, dimg.ctypes.data, len(img) - 40, out.ctypes.data, n + 64,
                                    allow=(gh.capi.GH_ERR_NO_EOF,))
     assert rc == gh.capi.GH_ERR_NO_EOF
+
+
+def test_emulated_staged_entry_points(emu, ctx, oracle):
+    """the four-step calls the C++ adapters make (gh_stage_input / gh_encode_staged / gh_stage_payload / gh_decode_staged)"""
+    import golden_huffman_b200 as gh
+    data = make_input("tile_plus1_4097")
+    n = len(data)
+    src = np.frombuffer(data, dtype=np.uint8).copy()
+    hist = np.zeros(256, dtype=np.uint64)
+    emu.check(emu.lib.gh_stage_input(ctx, src.ctypes.data, n, hist.ctypes.data), "gh_stage_input")
+    assert (hist == oracle.histogram(data)).all()
+    code = emu.build_code(hist)
+    rc, img = oracle.compress(data)
+    hdr = emu.write_header(code)
+    out = np.zeros(n * 4 + 64, dtype=np.uint8)
+    nb = C.c_uint64(0)
+    emu.check(emu.lib.gh_encode_staged(ctx, C.byref(code), out.ctypes.data, out.size, C.byref(nb)), "gh_encode_staged")
+    assert hdr + out[: nb.value].tobytes() == img
+    payload = np.frombuffer(img[len(hdr):], dtype=np.uint8).copy()
+    nsym = C.c_uint64(0)
+    emu.check(emu.lib.gh_stage_payload(ctx, payload.ctypes.data, payload.size, C.byref(code), C.byref(nsym)), "gh_stage_payload")
+    assert nsym.value == n
+    back = np.zeros(n, dtype=np.uint8)
+    emu.check(emu.lib.gh_decode_staged(ctx, back.ctypes.data, n), "gh_decode_staged")
+    assert back.tobytes() == data

@@ -218,21 +218,6 @@ int build_decode_tables(const gh_code* code, DecodeTables* t) {
     t->first_code_lj[len] = fc >= (1ull << len) ? 0xFFFFFFFFu : uint32_t(fc << (32 - len));
     t->start_pos[len] = code->start_pos[len];
   }
-  // Replay "v = (v << 1) | bit; ++len; if (v >= first_code_[len]) -> symbol" for every window value.
-  for (uint32_t w = 0; w < uint32_t(kDecLutSize); ++w) {
-    uint32_t v = 0;
-    uint16_t entry = 0;
-    for (uint32_t len = 1; len <= uint32_t(kDecLutBits) && len <= max_len; ++len) {
-      v = (v << 1) | ((w >> (kDecLutBits - len)) & 1u);
-      if (v >= code->first_code[len]) {  // below min_len first_code_ holds the 1024 sentinel: never true
-        uint32_t idx = code->start_pos[len] + (v - code->first_code[len]);
-        uint32_t sym = idx < GH_NSYM ? t->symbol[idx] : GH_EOF_SYMBOL;
-        entry = uint16_t((sym << 6) | len);
-        break;
-      }
-    }
-    t->lut[w] = entry;
-  }
   return GH_OK;
 }
 

@@ -9,26 +9,30 @@
 
 namespace gh {
 
-// ---- decode tables handed to the device (built on the host from a gh_code) -------------------------
-// Primary LUT indexed by the next kDecLutBits bits of the stream (MSB-first).
-//   entry = (symbol << 6) | length      length in 1..kDecLutBits : codeword fully inside the window
-//   entry = 0                           the codeword is longer than the window -> search first_code[]
-// This is the device analogue of TableCanonicalHuffDecoder::lookup_table_
-// (reference include/canonical_huff_encoder.cc:466-516) with the symbol folded in.
-constexpr int kDecLutBits = 12;
-constexpr int kDecLutSize = 1 << kDecLutBits;
+// ---- decode tables -----------------------------------------------------------------------------------------
+// The host hands the device only the small canonical tables of the header; the lookup tables are expanded from
+// them ON THE DEVICE (dec_build_luts_kernel) so no per-call host work grows with the table size:
+//   lut1  2^12 x u16   one codeword per lookup: (symbol << 6) | length, 0 = codeword longer than 12 bits.
+//                      The device analogue of TableCanonicalHuffDecoder::lookup_table_
+//                      (reference include/canonical_huff_encoder.cc:466-516) with the symbol folded in.
+//   lutC  2^15 x u8    as many whole codewords as fit in 15 bits (never the end mark): (count << 4) | total length,
+//                      0 = the first codeword does not fit or is the end mark. Used where only counts matter.
+//   lutW  2^13 x u32   up to 3 whole codewords in 13 bits: total length | count << 4 | symbols << 8 (first symbol
+//                      in the lowest byte), 0 = first codeword does not fit or is the end mark.
+constexpr int kLut1Bits = 12;
+constexpr int kLutCBits = 15;
+constexpr int kLutWBits = 13;
+constexpr int kLutWMaxSyms = 3;
 
 struct DecodeTables {
-  uint16_t lut[kDecLutSize];
   uint32_t first_code_lj[34];  // first_code_[len] << (32 - len), "left-justified" as in FastCanonicalHuffDecoder
-                               // (reference include/canonical_huff_encoder.cc:437-438); [33] = 0 guard
+                               // (reference include/canonical_huff_encoder.cc:437-438); 0xFFFFFFFF = no code of this length
   uint32_t start_pos[34];
   uint16_t symbol[GH_NSYM + 3];  // symbol_[] clamped to 0..256 (unused slots -> 256)
   uint32_t min_len, max_len;
 };
 
-// Fills `t` from `code` by replaying the reference's bit-serial rule
-// (include/canonical_huff_encoder.cc:396-402) on every kDecLutBits-bit prefix.
+// Fills `t` from `code` (header view: symbol_, min/max_len, start_pos_, first_code_).
 int build_decode_tables(const gh_code* code, DecodeTables* t);
 
 // ---- encode table: (codeword, length) per byte + the end mark, passed to kernels by value -----------

@@ -290,20 +290,23 @@ def main():
         C_ = comp_total
         alg = {  # algorithmic bytes per launch (DESIGN.md "roofline accounting")
             "hist_kernel": n, "encode_kernel": n + C_, "encode_stitch_kernel": 0,
-            "dec_speculate_kernel": C_, "dec_sync_kernel": 0, "dec_tile_sum_kernel": 0, "dec_offsets_kernel": 0,
+            "dec_build_luts_kernel": 0, "dec_speculate_kernel": C_, "dec_sync_kernel": 0, "dec_tile_sum_kernel": 0, "dec_offsets_kernel": 0,
             "dec_write_kernel": C_ + n,
         }
+        def alg_bytes(name):
+            return alg.get(name.split("<")[0], 0)
+
         for name, (cnt, ms) in prof.items():
             avg = ms / cnt
-            kernels[name] = {"launches_per_step": cnt / prof_steps, "avg_ms": avg,
-                             "GBps": (alg.get(name, 0) / (avg * 1e-3) / 1e9) if avg > 0 else None}
+            kernels[name] = {"launches_per_step": cnt / prof_steps, "avg_ms": avg, "ms_per_step": ms / prof_steps,
+                             "GBps": (alg_bytes(name) / (avg * 1e-3) / 1e9) if avg > 0 else None}
         if prof:
             dom = max(prof, key=lambda k: prof[k][1])
             avg = prof[dom][1] / prof[dom][0]
-            ach = alg.get(dom, 0) / (avg * 1e-3) / 1e9
+            ach = alg_bytes(dom) / (avg * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
                         "frac": ach / peak_gbs, "traffic": None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": alg.get(dom, 0), "avg_launch_ms": avg}
+                        "algorithmic_bytes_per_launch": alg_bytes(dom), "avg_launch_ms": avg}
     stage_roofline = {
         "encode": {"algorithmic_bytes": 2 * n_total + comp_total, "GBps": (2 * n_total + comp_total) * args.steps / (enc_ms * 1e-3) / 1e9},
         "decode": {"algorithmic_bytes": comp_total + n_total, "GBps": (comp_total + n_total) * args.steps / (dec_ms * 1e-3) / 1e9},

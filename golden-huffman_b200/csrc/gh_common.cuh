@@ -47,8 +47,24 @@ __device__ __forceinline__ u32 be32(u32 little_endian_word) { return __byte_perm
 // 128-bit read-only load (LDG.E.128.CONSTANT)
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
 
-__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
-__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
+// Single-word flag|value messages between thread blocks: relaxed, GPU scope (served by L2, no system-scope
+// round trip). One 64-bit word carries flag and value together, so no fence is needed around them.
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
+#ifdef GH_EMUL
+  return __atomic_load_n(p, __ATOMIC_SEQ_CST);
+#else
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
+#ifdef GH_EMUL
+  __atomic_store_n(p, v, __ATOMIC_SEQ_CST);
+#else
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
 
 // inclusive warp scan (Kogge-Stone over shuffles)
 __device__ __forceinline__ u32 warp_inclusive_scan(u32 v, unsigned lane) {

@@ -15,12 +15,14 @@
 //                    never meet inside the subsequence its exit changes and the round is marked dirty.
 //                    Rounds repeat until one is clean; the fixed point is exactly the serial decoder's path
 //                    because entry_0 is exact and every other entry equals its predecessor's exit.
-//                    If many rounds stay dirty (codes that synchronise slowly, e.g. near-fixed-length ones),
-//                    S is multiplied by 4 and the process restarts; at S = whole payload it is the serial walk.
+//                    Round k makes subsequences 0..k exact whatever the data, so termination and exactness are
+//                    unconditional; codes that synchronise slowly (near-fixed-length ones) just take more rounds,
+//                    each touching fewer subsequences.
 //   K6   offsets   : first end mark on the true path truncates the counts; exclusive scan -> output offsets.
-//   K7   write     : every thread re-decodes its subsequence from its now-exact entry with the 12-bit LUT
-//                    (long codes: left-justified first_code search, as the reference's Fast decoder does) and
-//                    stores symbols 16 at a time with 128-bit stores.
+//   K7   write     : every thread re-decodes its subsequence from its now-exact entry, up to 3 codewords per
+//                    13-bit table lookup (long codes: left-justified first_code search, as the reference's Fast
+//                    decoder does), and stores symbols 16 at a time with 128-bit stores.
+// The lookup tables are expanded from the header's canonical tables by a kernel (dec_build_luts_kernel).
 //
 // Algorithmic traffic: C bytes read + N bytes written; this implementation reads the payload twice
 // (speculate + write), which the roofline accounting in bench.py does NOT credit.
@@ -28,14 +30,17 @@
 
 namespace gh {
 
-constexpr int kDecThreads = 256;
+constexpr int kDecThreads = 256;   // threads per block = subsequences per tile, all decode kernels
 constexpr u32 kNoEof = 0xffffffffu;
 constexpr u32 kMinSubBytes = 128;
 constexpr u32 kMaxSubBytes = 1u << 27;
-constexpr int kRoundsBeforeEscalation = 12;
 
 // per-subsequence state, one 64-bit word so it is read and written atomically
 //   [31:0] count   [47:32] entry   [55:48] exit   [56] eof
+// A path is the codeword chain that starts at bit `entry` of the subsequence. It runs THROUGH end marks (a
+// mis-phased path meets bit patterns that look like the end mark all the time; stopping there would throw away
+// the exit it needs to synchronise): `eof` says the path contains an end mark, `count` is the number of symbols
+// before the first one (all symbols if there is none), `exit` is where the path leaves the subsequence.
 __host__ __device__ inline u64 pack_state(u32 count, u32 entry, u32 exit, u32 eof) {
   return u64(count) | (u64(entry & 0xffffu) << 32) | (u64(exit & 0xffu) << 48) | (u64(eof & 1u) << 56);
 }
@@ -46,17 +51,20 @@ __host__ __device__ inline u32 st_eof(u64 s) { return u32(s >> 56) & 1u; }
 
 struct DecControl {  // device-resident, copied back to the host after each round
   u32 changed;
-  u32 eof_index;  // first subsequence (in order) whose path ends in the end mark
+  u32 eof_index;  // first subsequence (in order) whose path contains the end mark
   u64 total;      // symbols before that end mark
   u32 exit_bit;
   u32 eof_found;
   u32 sub_bytes;
-  u32 pad_;
+  u32 unmerged;  // walks of the last round that never met the stored path
   u64 n_sub;
 };
 
 struct DecWorkspace {
-  const DecodeTables* tables;
+  const DecodeTables* tables;  // small canonical tables (host-built)
+  const uint16_t* lut1;        // [2^12]  device-built, see gh_internal.h
+  const uint8_t* lutC;         // [2^15]
+  const u32* lutW;             // [2^13]
   DecControl* ctl;
   u64* sub;        // [n_sub]
   u64* tile_sum;   // [n_tiles]
@@ -72,89 +80,141 @@ struct DecGeometry {
   u32 entry0;
 };
 
-// ---- shared-memory copy of the decode tables --------------------------------------------------------
-struct SmemTables {
-  uint16_t lut[kDecLutSize];
+// ---- canonical decode rule on the small tables ---------------------------------------------------------------
+struct SmemCanon {
   u32 first_code_lj[34];
   u32 start_pos[34];
   uint16_t symbol[GH_NSYM + 3];
-  u32 max_len;
+  u32 min_len, max_len;
 };
 
-__device__ __forceinline__ void load_tables(SmemTables& s, const DecodeTables* __restrict__ g) {
-  for (unsigned i = threadIdx.x; i < kDecLutSize / 2; i += blockDim.x)
-    reinterpret_cast<u32*>(s.lut)[i] = reinterpret_cast<const u32*>(g->lut)[i];
+__device__ __forceinline__ void load_canon(SmemCanon& s, const DecodeTables* __restrict__ g) {
   for (unsigned i = threadIdx.x; i < 34; i += blockDim.x) {
     s.first_code_lj[i] = g->first_code_lj[i];
     s.start_pos[i] = g->start_pos[i];
   }
   for (unsigned i = threadIdx.x; i < GH_NSYM + 3; i += blockDim.x) s.symbol[i] = g->symbol[i];
-  if (threadIdx.x == 0) s.max_len = g->max_len;
-  __syncthreads();
-}
-
-// One codeword from the next 32 stream bits (left-justified in `window`).
-__device__ __forceinline__ void decode_one(const SmemTables& s, u32 window, u32& sym, u32& len) {
-  const u32 e = s.lut[window >> (32 - kDecLutBits)];
-  len = e & 63u;
-  sym = e >> 6;
-  if (len == 0) {
-    // longer than the LUT window: smallest len with window >= first_code[len] << (32 - len)
-    // (reference include/canonical_huff_encoder.h:157-162 cfind on the left-justified table)
-    len = kDecLutBits + 1;
-    const u32 max_len = s.max_len;
-    while (len < max_len && window < s.first_code_lj[len]) ++len;
-    u32 idx = s.start_pos[len] + ((window - s.first_code_lj[len]) >> (32 - len));
-    idx = idx < u32(GH_NSYM) ? idx : u32(GH_NSYM - 1);
-    sym = s.symbol[idx];
+  if (threadIdx.x == 0) {
+    s.min_len = g->min_len;
+    s.max_len = g->max_len;
   }
 }
 
-// ---- MSB-first bit reader over global memory, 128-bit loads --------------------------------------------
+// Smallest len in [from, max_len] with window >= first_code[len] << (32 - len): the reference's rule
+// (include/canonical_huff_encoder.cc:396-402) on the left-justified table (its Fast decoder, :437-453 / cfind).
+__device__ __forceinline__ void canon_search(const SmemCanon& s, u32 window, u32 from, u32& sym, u32& len) {
+  len = from;
+  const u32 max_len = s.max_len;
+  while (len < max_len && window < s.first_code_lj[len]) ++len;
+  u32 idx = s.start_pos[len] + ((window - s.first_code_lj[len]) >> (32 - len));
+  idx = idx < u32(GH_NSYM) ? idx : u32(GH_NSYM - 1);
+  sym = s.symbol[idx];
+}
+
+// One codeword from the next 32 stream bits (left-justified in `window`) through the 12-bit table.
+__device__ __forceinline__ void decode_one(const SmemCanon& s, const uint16_t* lut1, u32 window, u32& sym, u32& len) {
+  const u32 e = lut1[window >> (32 - kLut1Bits)];
+  len = e & 63u;
+  sym = e >> 6;
+  if (len == 0) canon_search(s, window, kLut1Bits + 1, sym, len);
+}
+
+// ---- K5 prologue: expand the canonical tables into the lookup tables, on the device -------------------------
+// thread w handles window value w of each table it is in range for
+__global__ void __launch_bounds__(256)
+dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restrict__ lut1, uint8_t* __restrict__ lutC,
+                      u32* __restrict__ lutW) {
+  __shared__ SmemCanon s;
+  load_canon(s, tables);
+  __syncthreads();
+  const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 min_len = s.min_len;
+  // walk whole codewords inside a k-bit window value v (left-justified), stopping at the end mark
+  auto walk = [&](u32 v, int k, int max_syms, u32& total_len, u32& nsym, u32& packed) {
+    total_len = 0, nsym = 0, packed = 0;
+    u32 win = v << (32 - k);
+    int avail = k;
+    while (int(nsym) < max_syms) {
+      if (avail < int(min_len)) break;
+      u32 sym, len;
+      canon_search(s, win, min_len, sym, len);
+      if (int(len) > avail || sym == u32(GH_EOF_SYMBOL)) break;
+      if (nsym < 3) packed |= (sym & 0xffu) << (8 * nsym);
+      ++nsym;
+      total_len += len;
+      win = len < 32 ? win << len : 0u;
+      avail -= int(len);
+    }
+  };
+  u32 tl, ns, pk;
+  if (w < (1u << kLutCBits)) {
+    walk(w, kLutCBits, 15, tl, ns, pk);
+    lutC[w] = uint8_t(ns ? ((ns << 4) | tl) : 0u);
+  }
+  if (w < (1u << kLutWBits)) {
+    walk(w, kLutWBits, kLutWMaxSyms, tl, ns, pk);
+    lutW[w] = ns ? (tl | (ns << 4) | (pk << 8)) : 0u;
+  }
+  if (w < (1u << kLut1Bits)) {
+    // single codeword, end mark included (as symbol 256); 0 when it does not fit in 12 bits
+    u32 sym, len;
+    canon_search(s, w << (32 - kLut1Bits), min_len, sym, len);
+    lut1[w] = uint16_t(len <= u32(kLut1Bits) ? ((sym << 6) | len) : 0u);
+  }
+}
+
+// ---- MSB-first bit reader over global memory --------------------------------------------------------------
+// Each lane streams its own subsequence with 128-bit loads. The four words of the current vector sit in
+// registers and are rotated as they are consumed, so the refill is straight-line code (a few predicated
+// instructions) instead of a chain of branches: with 32 lanes refilling at different symbols, some lane needs
+// a refill on almost every iteration, so whatever the refill costs is paid by the whole warp every time.
+__device__ __noinline__ uint4 fetch_tail(const uint8_t* bytes, u64 readable, u64 v) {
+  u32 w[4];
+  for (int k = 0; k < 4; ++k) {
+    u32 x = 0;
+    for (int b = 0; b < 4; ++b) {
+      const u64 idx = v * 16 + u64(k * 4 + b);
+      const u32 byte = idx < readable ? u32(bytes[idx]) : 0xffu;  // past the end: the reference's 1-padding
+      x |= byte << (8 * b);
+    }
+    w[k] = x;
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 struct BitReader {
   const uint8_t* bytes;
   u64 readable;
-  u64 vi;     // index of the 16-byte vector held in `cur`
-  uint4 cur;
-  u32 wpos;   // next 32-bit word of `cur` to hand out
-  u64 buf;    // next `avail` stream bits, left-justified
-  int avail;  // kept >= 32 between symbols
+  u64 full_vecs;  // vectors that lie entirely inside the readable range
+  u64 vi;         // index of the NEXT vector to load
+  u32 w0, w1, w2, w3;  // upcoming 32-bit words (stream order), w0 first
+  u32 left;            // how many of them are still unread (1..4)
+  u64 buf;             // next `avail` stream bits, left-justified
+  int avail;           // kept >= 32 between symbols
 
-  __device__ __forceinline__ uint4 fetch(u64 v) const {
-    if ((v + 1) * 16 <= readable) return ldg128(reinterpret_cast<const uint4*>(bytes) + v);
-    u32 w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      u32 x = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const u64 idx = v * 16 + u64(k * 4 + b);
-        const u32 byte = idx < readable ? u32(bytes[idx]) : 0xffu;  // past the end: the reference's 1-padding
-        x |= byte << (8 * b);
-      }
-      w[k] = x;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  __device__ __forceinline__ u32 next_word() {
-    const u32 w = wpos == 0 ? cur.x : wpos == 1 ? cur.y : wpos == 2 ? cur.z : cur.w;
-    if (++wpos == 4) {
-      wpos = 0;
-      ++vi;
-      cur = fetch(vi);
-    }
-    return be32(w);
+  __device__ __forceinline__ void load_next() {
+    uint4 v;
+    if (vi < full_vecs) v = ldg128(reinterpret_cast<const uint4*>(bytes) + vi);
+    else v = fetch_tail(bytes, readable, vi);
+    ++vi;
+    w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+    left = 4;
   }
   __device__ __forceinline__ void push() {
-    buf |= u64(next_word()) << (32 - avail);
+    buf |= u64(be32(w0)) << (32 - avail);
     avail += 32;
+    w0 = w1, w1 = w2, w2 = w3;
+    if (--left == 0) load_next();
   }
   __device__ __forceinline__ void seek(const uint8_t* base, u64 readable_bytes, u64 bitpos) {
     bytes = base;
     readable = readable_bytes;
+    full_vecs = readable_bytes >> 4;
     vi = bitpos >> 7;
-    cur = fetch(vi);
-    wpos = u32(bitpos >> 5) & 3u;
+    load_next();
+    const u32 skip = u32(bitpos >> 5) & 3u;  // words of this vector that lie before bitpos
+    for (u32 k = 0; k < skip; ++k) w0 = w1, w1 = w2, w2 = w3;
+    left = 4 - skip;
     buf = 0;
     avail = 0;
     push();
@@ -179,90 +239,148 @@ __device__ __forceinline__ u64 sub_end_bits(const DecGeometry& g, u64 i) {
 }
 
 // ---- K5a: speculative decode of every subsequence from bit 0 (subsequence 0: from the true entry) ---------
+// Only counts are needed here, so the walk takes as many whole codewords per lookup as fit in 15 bits.
+struct SmemSpeculate {
+  SmemCanon canon;
+  uint16_t lut1[1 << kLut1Bits];
+  uint8_t lutC[1 << kLutCBits];
+};
+
 __global__ void __launch_bounds__(kDecThreads)
 dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
-  __shared__ SmemTables s;
-  load_tables(s, ws.tables);
+  __shared__ SmemSpeculate s;
+  load_canon(s.canon, ws.tables);
+  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
+    reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
+  for (unsigned i = threadIdx.x; i < (1u << kLutCBits) / 16; i += kDecThreads)
+    reinterpret_cast<uint4*>(s.lutC)[i] = reinterpret_cast<const uint4*>(ws.lutC)[i];
+  __syncthreads();
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
   if (i >= g.n_sub) return;
   const u64 start = i * u64(g.sub_bytes) * 8;
   const u32 end = u32(sub_end_bits(g, i));
   const u32 entry = (i == 0) ? g.entry0 : 0u;
-  u32 pos = entry, count = 0, eof = 0;
+  u32 pos = entry, count = 0, eof = 0, count_at_eof = 0;
   BitReader r;
   r.seek(g.payload, g.readable, start + pos);
+  // (a) multi-codeword steps while a full 15-bit window lies inside the subsequence: nothing taken from the
+  //     table can cross `end`, so the first boundary at or after `end` is found exactly by (b)
+  if (end >= u32(kLutCBits)) {
+    const u32 last = end - u32(kLutCBits);
+    while (pos <= last) {
+      const u32 win = r.window();
+      const u32 e = s.lutC[win >> (32 - kLutCBits)];
+      u32 len;
+      if (e) {
+        len = e & 15u;
+        count += e >> 4;
+      } else {  // first codeword longer than 15 bits, or the end mark
+        u32 sym;
+        decode_one(s.canon, s.lut1, win, sym, len);
+        if (sym == u32(GH_EOF_SYMBOL)) {
+          if (!eof) eof = 1, count_at_eof = count;
+        } else {
+          ++count;
+        }
+      }
+      pos += len;
+      r.consume(len);
+    }
+  }
+  // (b) single codewords up to the crossing
   while (pos < end) {
     u32 sym, len;
-    decode_one(s, r.window(), sym, len);
+    decode_one(s.canon, s.lut1, r.window(), sym, len);
     if (sym == u32(GH_EOF_SYMBOL)) {
-      eof = 1;
-      break;
+      if (!eof) eof = 1, count_at_eof = count;
+    } else {
+      ++count;
     }
-    ++count;
     pos += len;
     r.consume(len);
   }
-  ws.sub[i] = pack_state(count, entry, eof ? 0u : pos - end, eof);
+  ws.sub[i] = pack_state(eof ? count_at_eof : count, entry, pos - end, eof);
 }
 
 // ---- K5b: one synchronisation round ------------------------------------------------------------------------
+struct SmemSync {
+  SmemCanon canon;
+  uint16_t lut1[1 << kLut1Bits];
+};
+
 __global__ void __launch_bounds__(kDecThreads)
 dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
-  __shared__ SmemTables s;
-  load_tables(s, ws.tables);
+  __shared__ SmemSync s;
+  load_canon(s.canon, ws.tables);
+  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
+    reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
+  __syncthreads();
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
-  if (i >= g.n_sub) return;
-  const u64 mine = ld_volatile_u64(ws.sub + i);
-  const u32 want = (i == 0) ? g.entry0 : st_exit(ld_volatile_u64(ws.sub + i - 1));
-  if (want == st_entry(mine)) return;
-
-  const u64 start = i * u64(g.sub_bytes) * 8;
-  const u32 end = u32(sub_end_bits(g, i));
-  // path A = the stored one (from st_entry(mine)), path B = the one we now believe in (from `want`)
-  u32 pos_a = st_entry(mine), pos_b = want;
-  u32 steps_a = 0, steps_b = 0, eof_b = 0;
-  bool merged = false;
-  BitReader ra, rb;
-  ra.seek(g.payload, g.readable, start + pos_a);
-  rb.seek(g.payload, g.readable, start + pos_b);
-  while (pos_b < end) {
-    if (pos_a == pos_b) {
-      merged = true;
-      break;
-    }
-    u32 sym, len;
-    if (pos_a < pos_b) {  // A is behind (hence still inside the subsequence): advance it
-      decode_one(s, ra.window(), sym, len);
-      if (sym == u32(GH_EOF_SYMBOL)) {
-        pos_a = 0xffffffffu;  // A ended in an end mark: it can never meet B
-      } else {
-        ++steps_a;
-        pos_a += len;
-        ra.consume(len);
-      }
-    } else {
-      decode_one(s, rb.window(), sym, len);
-      if (sym == u32(GH_EOF_SYMBOL)) {
-        eof_b = 1;
+  u64 mine = 0;
+  u32 want = 0;
+  bool stale = false;
+  if (i < g.n_sub) {
+    mine = ld_volatile_u64(ws.sub + i);
+    want = (i == 0) ? g.entry0 : st_exit(ld_volatile_u64(ws.sub + i - 1));
+    stale = want != st_entry(mine);
+  }
+  bool merged = true;
+  if (stale) {
+    const u64 start = i * u64(g.sub_bytes) * 8;
+    const u32 end = u32(sub_end_bits(g, i));
+    // path A = the stored one (from st_entry(mine)), path B = the one we now believe in (from `want`).
+    // Always step the one that is behind; where they meet, the rest of A's stored result is B's.
+    u32 pos_a = st_entry(mine), pos_b = want;
+    u32 steps_a = 0, steps_b = 0, eof_b = 0, count_b_at_eof = 0;
+    bool a_usable = true;  // false once A has run through an end mark: its stored count stops there
+    merged = false;
+    BitReader ra, rb;
+    ra.seek(g.payload, g.readable, start + pos_a);
+    rb.seek(g.payload, g.readable, start + pos_b);
+    while (pos_b < end) {
+      if (a_usable && pos_a == pos_b) {
+        merged = true;
         break;
       }
-      ++steps_b;
-      pos_b += len;
-      rb.consume(len);
+      u32 sym, len;
+      if (a_usable && pos_a < pos_b) {
+        decode_one(s.canon, s.lut1, ra.window(), sym, len);
+        if (sym == u32(GH_EOF_SYMBOL)) a_usable = false;
+        else ++steps_a;
+        pos_a += len;
+        ra.consume(len);
+      } else {
+        decode_one(s.canon, s.lut1, rb.window(), sym, len);
+        if (sym == u32(GH_EOF_SYMBOL)) {
+          if (!eof_b) eof_b = 1, count_b_at_eof = steps_b;
+        } else {
+          ++steps_b;
+        }
+        pos_b += len;
+        rb.consume(len);
+      }
     }
+    u32 count, exit, eof;
+    if (merged) {
+      exit = st_exit(mine);
+      if (eof_b) {
+        eof = 1, count = count_b_at_eof;
+      } else {  // A had no end mark before the meeting point, so its stored count/eof continue B's
+        eof = st_eof(mine);
+        count = steps_b + (st_count(mine) - steps_a);
+      }
+    } else {
+      exit = pos_b - end;
+      eof = eof_b;
+      count = eof_b ? count_b_at_eof : steps_b;
+    }
+    st_volatile_u64(ws.sub + i, pack_state(count, want, exit, eof));
+    if (exit != st_exit(mine) || eof != st_eof(mine)) ws.ctl->changed = 1u;
   }
-  u32 count, exit, eof;
-  if (merged) {  // from the meeting point on, the stored path is the true one
-    count = steps_b + (st_count(mine) - steps_a);
-    exit = st_exit(mine);
-    eof = st_eof(mine);
-  } else {
-    count = steps_b;
-    eof = eof_b;
-    exit = eof_b ? 0u : pos_b - end;
-  }
-  st_volatile_u64(ws.sub + i, pack_state(count, want, exit, eof));
-  if (exit != st_exit(mine) || eof != st_eof(mine)) ws.ctl->changed = 1u;
+  // how many walks ran to the end of their subsequence without meeting the stored path: the host uses the
+  // fraction after the first round to decide whether this code needs coarser subsequences
+  const unsigned lost = __ballot_sync(0xffffffffu, !merged);
+  if ((threadIdx.x & 31) == 0 && lost) atomicAdd(&ws.ctl->unmerged, u32(__popc(lost)));
 }
 
 // ---- K6: truncate at the first end mark, turn counts into output offsets -----------------------------------
@@ -340,12 +458,24 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
   }
 }
 
-// ---- K7: final decode from the exact entries, 128-bit stores ---------------------------------------------
+// ---- K7: final decode from the exact entries ------------------------------------------------------------------
+// Up to 3 codewords per lookup (13-bit window); symbols are collected 8 at a time in a 64-bit register and two
+// such registers leave as one 128-bit store (16-byte aligned: the first few symbols go out as bytes).
+struct SmemWrite {
+  SmemCanon canon;
+  uint16_t lut1[1 << kLut1Bits];
+  u32 lutW[1 << kLutWBits];
+  u32 warp_total[kDecThreads / 32];
+};
+
 __global__ void __launch_bounds__(kDecThreads)
 dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
-  __shared__ SmemTables s;
-  __shared__ u32 s_warp[kDecThreads / 32];
-  load_tables(s, ws.tables);
+  __shared__ SmemWrite s;
+  load_canon(s.canon, ws.tables);
+  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
+    reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
+  for (unsigned i = threadIdx.x; i < (1u << kLutWBits) / 4; i += kDecThreads)
+    reinterpret_cast<uint4*>(s.lutW)[i] = reinterpret_cast<const uint4*>(ws.lutW)[i];
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const u64 i = u64(blockIdx.x) * kDecThreads + t;
   const u32 eof_index = ws.ctl->eof_index;
@@ -356,12 +486,12 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
     count = st_count(st);
   }
   const u32 incl = warp_inclusive_scan(count, lane);
-  if (lane == 31) s_warp[warp] = incl;
+  if (lane == 31) s.warp_total[warp] = incl;
   __syncthreads();
   u32 warp_base = 0;
 #pragma unroll
   for (int k = 0; k < kDecThreads / 32; ++k)
-    if (unsigned(k) < warp) warp_base += s_warp[k];
+    if (unsigned(k) < warp) warp_base += s.warp_total[k];
   const u64 o = ws.tile_base[blockIdx.x] + warp_base + (incl - count);
   if (count == 0 || o >= out_cap) return;
   u64 remaining = count;
@@ -371,26 +501,58 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   r.seek(g.payload, g.readable, i * u64(g.sub_bytes) * 8 + st_entry(st));
   uint8_t* dst = out + o;
   u32 sym, len;
+  // head: single symbols up to the first 16-byte boundary of the output
   while (remaining && (reinterpret_cast<uintptr_t>(dst) & 15)) {
-    decode_one(s, r.window(), sym, len);
+    decode_one(s.canon, s.lut1, r.window(), sym, len);
     r.consume(len);
     *dst++ = uint8_t(sym);
     --remaining;
   }
-  while (remaining >= 16) {
-    u32 w[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      decode_one(s, r.window(), sym, len);
-      r.consume(len);
-      w[k >> 2] |= (sym & 0xffu) << (8 * (k & 3));
+  // body: `acc` collects symbols (first symbol in the lowest byte); every 8 symbols it is retired, every second
+  // retirement is a 128-bit store
+  u64 acc = 0, held = 0;
+  u32 nacc = 0;      // symbols in acc (0..7 between steps)
+  bool have_held = false;
+  while (remaining >= u64(kLutWMaxSyms)) {  // any table entry yields at most kLutWMaxSyms symbols
+    const u32 win = r.window();
+    const u32 e = s.lutW[win >> (32 - kLutWBits)];
+    u32 n, syms;
+    if (e) {
+      len = e & 15u;
+      n = (e >> 4) & 3u;
+      syms = e >> 8;
+    } else {  // codeword longer than 13 bits (the end mark cannot occur: the count stops before it)
+      decode_one(s.canon, s.lut1, win, sym, len);
+      n = 1;
+      syms = sym & 0xffu;
     }
-    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-    dst += 16;
-    remaining -= 16;
+    r.consume(len);
+    remaining -= n;
+    const u32 sh = nacc * 8;
+    acc |= u64(syms) << sh;
+    nacc += n;
+    if (nacc >= 8) {
+      const u64 spill = sh > 40 ? u64(syms) >> (64 - sh) : 0ull;  // bytes that did not fit
+      if (have_held) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(u32(held), u32(held >> 32), u32(acc), u32(acc >> 32));
+        dst += 16;
+        have_held = false;
+      } else {
+        held = acc;
+        have_held = true;
+      }
+      acc = spill;
+      nacc -= 8;
+    }
   }
+  // drain what is collected, then the last few symbols one by one
+  if (have_held) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held), u32(held >> 32));
+    dst += 8;
+  }
+  for (u32 k = 0; k < nacc; ++k) *dst++ = uint8_t(acc >> (8 * k));
   while (remaining) {
-    decode_one(s, r.window(), sym, len);
+    decode_one(s.canon, s.lut1, r.window(), sym, len);
     r.consume(len);
     *dst++ = uint8_t(sym);
     --remaining;
@@ -399,7 +561,7 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
 
 // ---- host orchestration -------------------------------------------------------------------------------
 struct DecLayout {
-  size_t off_tables, off_ctl, off_sub, off_tile_sum, off_tile_base, total;
+  size_t off_tables, off_lut1, off_lutC, off_lutW, off_ctl, off_sub, off_tile_sum, off_tile_base, total;
 };
 
 static DecLayout dec_layout(u64 slice_bytes) {
@@ -408,7 +570,10 @@ static DecLayout dec_layout(u64 slice_bytes) {
   const u64 max_tiles = max_sub / kDecThreads + 2;
   DecLayout L;
   L.off_tables = 0;
-  L.off_ctl = up(sizeof(DecodeTables));
+  L.off_lut1 = up(sizeof(DecodeTables));
+  L.off_lutC = L.off_lut1 + up(sizeof(uint16_t) << kLut1Bits);
+  L.off_lutW = L.off_lutC + up(sizeof(uint8_t) << kLutCBits);
+  L.off_ctl = L.off_lutW + up(sizeof(u32) << kLutWBits);
   L.off_sub = L.off_ctl + 256;
   L.off_tile_sum = L.off_sub + up(size_t(max_sub) * 8);
   L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
@@ -420,6 +585,9 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   uint8_t* p = static_cast<uint8_t*>(d_ws);
   DecWorkspace w;
   w.tables = reinterpret_cast<const DecodeTables*>(p + L.off_tables);
+  w.lut1 = reinterpret_cast<const uint16_t*>(p + L.off_lut1);
+  w.lutC = reinterpret_cast<const uint8_t*>(p + L.off_lutC);
+  w.lutW = reinterpret_cast<const u32*>(p + L.off_lutW);
   w.ctl = reinterpret_cast<DecControl*>(p + L.off_ctl);
   w.sub = reinterpret_cast<u64*>(p + L.off_sub);
   w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
@@ -469,6 +637,8 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     int rc = build_decode_tables(code, &tables);
     if (rc != GH_OK) return rc;
     GH_CUDA_TRY(cudaMemcpyAsync(const_cast<DecodeTables*>(ws.tables), &tables, sizeof(tables), cudaMemcpyHostToDevice, stream));
+    GH_LAUNCH(dec_build_luts_kernel, (1u << kLutCBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
+              const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW));
     g.sub_bytes = choose_sub_bytes(slice_bytes);
   } else {
     GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
@@ -476,8 +646,13 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     g.sub_bytes = h_ctl.sub_bytes;
     if (g.sub_bytes < kMinSubBytes || (g.sub_bytes % kMinSubBytes)) return GH_ERR_ARG;
   }
-
-  u32 total_rounds = 0;
+  // Synchronisation rounds until a clean one. Round k makes subsequences 0..k exact whatever the data, so this
+  // terminates after at most n_sub rounds; with codes that self-synchronise it takes two or three.
+  // A code that synchronises slowly relative to the subsequence size (near-fixed-length codes: uniform bytes)
+  // shows up in the first round as many walks that never meet the stored path; the expected number of rounds is
+  // then log(n_sub) / log(1 / that fraction), so the subsequences are made 4x coarser (fraction -> fraction^4)
+  // and the speculation is redone -- one extra pass instead of dozens of rounds.
+  u32 rounds = 0;
   bool speculate = first_call != 0;
   while (true) {
     g.n_sub = (slice_bytes + g.sub_bytes - 1) / g.sub_bytes;
@@ -487,9 +662,8 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
       int rc = check_launch();
       if (rc != GH_OK) return rc;
     }
-    bool converged = false;
-    const bool can_escalate = g.sub_bytes < kMaxSubBytes && g.n_sub > 1;
-    for (int round = 0; !can_escalate || round < kRoundsBeforeEscalation; ++round) {
+    bool coarsen = false;
+    for (u32 level_round = 0;; ++level_round) {
       h_ctl = DecControl();
       h_ctl.eof_index = kNoEof;
       h_ctl.sub_bytes = g.sub_bytes;
@@ -500,17 +674,18 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
       if (rc != GH_OK) return rc;
       GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
       GH_CUDA_TRY(cudaStreamSynchronize(stream));
-      ++total_rounds;
-      if (!h_ctl.changed) {
-        converged = true;
+      ++rounds;
+      if (!h_ctl.changed) break;
+      if (level_round == 0 && speculate && g.n_sub >= 64 && u64(h_ctl.unmerged) * 16 > g.n_sub &&
+          g.sub_bytes < kMaxSubBytes) {
+        coarsen = true;
         break;
       }
+      if (u64(level_round) > g.n_sub + 2) return GH_ERR_FORMAT;  // cannot happen: see above
     }
-    if (converged) break;
-    // slow to synchronise at this granularity: coarser subsequences, start over
+    if (!coarsen) break;
     u64 bigger = u64(g.sub_bytes) * 4;
-    if (bigger > kMaxSubBytes) bigger = kMaxSubBytes;
-    g.sub_bytes = u32(bigger);
+    g.sub_bytes = u32(bigger > kMaxSubBytes ? kMaxSubBytes : bigger);
     speculate = true;
   }
 
@@ -520,7 +695,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     result->n_symbols = h_ctl.total;
     result->exit_bit = h_ctl.exit_bit;
     result->eof_found = h_ctl.eof_found;
-    result->rounds = total_rounds;
+    result->rounds = rounds;
     result->sub_bytes = g.sub_bytes;
   }
   if (geom_out) *geom_out = g;

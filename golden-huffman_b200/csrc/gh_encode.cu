@@ -5,21 +5,21 @@
 // Algorithmic traffic: N bytes read + C bytes written (the scan is fused by decoupled look-back, so the
 // input is not read a second time to learn the bit offsets).
 //
-// A tile is kEncThreads x 16 input bytes. Per tile:
-//   1. every thread loads one 128-bit vector (coalesced) and gathers (codeword, length) for its 16 bytes
-//      from the shared-memory LUT, keeping them in registers;
-//   2. the per-thread bit counts are scanned across the block (warp shuffles), the tile total is published
-//      and the tile's global bit offset G is obtained by a warp-wide decoupled look-back over the
-//      predecessors' (flag | value) words;
-//   3. each thread shifts its codewords into a 64-bit MSB-first accumulator and drops finished 32-bit
-//      words into a shared staging buffer whose word 0 is global word G/32 (so the tile is already
-//      phase-aligned with the output);
-//   4. the staged words are byte-swapped to stream order and stored coalesced. The tile's first word, when
-//      it is shared with the previous tile, is NOT stored: its bits go to head[tile] and a tiny second
-//      kernel ORs them into the word the previous tile wrote -- every output word has exactly one writer
-//      per kernel, no global atomics on the payload.
-// The thread that owns the last input byte also appends the end-of-encoding codeword and the 1-padding
-// (reference include/canonical_huff_encoder.cc:255-257).
+// Persistent blocks take tiles of kEncThreads x 16 input bytes from an atomic ticket. Per tile:
+//   1. every thread loads one 128-bit vector (coalesced), gathers (codeword, length) for its 16 bytes from the
+//      shared-memory LUT and concatenates them in registers into 64-bit chunks (4 codewords per chunk when
+//      no code is longer than 16 bits, 2 otherwise) -- `acc = (acc << len) | code`, three instructions a symbol;
+//   2. the per-thread bit counts are scanned across the block (warp shuffles); warp 0 publishes the tile total
+//      and resolves the tile's global bit offset G by a warp-wide decoupled look-back over the predecessors'
+//      (flag | value) words WHILE the other warps already pack: packing only needs tile-relative offsets;
+//   3. each chunk is left-justified and OR-ed into a zeroed shared staging buffer at its tile-relative bit
+//      position (shared-memory atomics: neighbouring chunks share words);
+//   4. copy-out: global word (G/32 + i) = funnel-shift of staged words i-1, i by (G mod 32) -- the phase
+//      alignment with the output costs one SHF per output word -- byte-swapped to stream order, coalesced.
+//      The tile's first word, when shared with the previous tile, is NOT stored: its bits go to head[tile] and
+//      a tiny second kernel ORs them into the word the previous tile wrote -- every output word has exactly
+//      one writer per kernel, no global atomics on the payload. The last tile adds the end-mark codeword and
+//      the 1-padding (reference include/canonical_huff_encoder.cc:255-257).
 #include "gh_common.cuh"
 
 namespace gh {
@@ -27,8 +27,9 @@ namespace gh {
 constexpr int kEncThreads = 256;
 constexpr int kEncBytesPerThread = 16;
 constexpr int kEncTileBytes = kEncThreads * kEncBytesPerThread;
-// worst case per tile: 4096 symbols x 32 bits + end mark 32 + padding 7 + phase 31
-constexpr int kEncStageWords = (kEncTileBytes * 32 + 32 + 7 + 31 + 31) / 32 + 1;
+// worst case per tile: 4096 symbols x 32 bits + end mark 32, plus one word of slack for the funnel shift
+constexpr int kEncStageWords = (kEncTileBytes * 32 + 32 + 31) / 32 + 2;
+constexpr int kEncBlocksPerSm = 6;
 
 constexpr u64 kFlagMask = 3ull << 62;
 constexpr u64 kFlagAggregate = 1ull << 62;  // value = bits of this tile only
@@ -37,16 +38,34 @@ constexpr u64 kFlagPrefix = 2ull << 62;     // value = global bit offset just af
 struct EncWorkspace {
   u64* tile_state;  // [ntiles]
   u32* head;        // [ntiles]
-  u32* ticket;      // tile dispenser (tiles are handed out in the order blocks become resident)
+  u32* ticket;      // tile dispenser (tiles are handed out in the order blocks ask for them)
 };
 
 __host__ __device__ inline u64 enc_num_tiles(u64 n) { return (n + kEncTileBytes - 1) / kEncTileBytes; }
 
+// the one partial vector at the end of the input (kept out of line: it runs once per launch)
+__device__ __noinline__ uint4 load_ragged(const uint8_t* p, int cnt) {
+  u32 w[4] = {0, 0, 0, 0};
+  for (int k = 0; k < cnt; ++k) w[k >> 2] |= u32(p[k]) << (8 * (k & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// OR the low `len` bits of `acc` (len in 1..64) into the staging bit string at bit position `pos`
+__device__ __forceinline__ void stage_bits(u32* stage, u32 pos, u64 acc, u32 len) {
+  const u64 v = acc << (64 - len);  // left-justified
+  const u32 w = pos >> 5, sh = pos & 31;
+  atomicOr(stage + w, u32(v >> 32) >> sh);
+  if (sh + len > 32) atomicOr(stage + w + 1, u32(v >> sh));
+  if (sh + len > 64) atomicOr(stage + w + 2, u32(v) << (32 - sh));
+}
+
+template <int kSymsPerChunk>
 __global__ void __launch_bounds__(kEncThreads)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
               u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
-  __shared__ u32 s_code[GH_NSYM + 3];
-  __shared__ uint8_t s_len[GH_NSYM + 3];
+  constexpr int kChunks = kEncBytesPerThread / kSymsPerChunk;
+  __shared__ u32 s_lut[GH_NSYM + 3];      // kSymsPerChunk == 4: (len << 16) | code ; else: code
+  __shared__ uint8_t s_len[GH_NSYM + 3];  // kSymsPerChunk == 2 only
   __shared__ u32 s_stage[kEncStageWords];
   __shared__ u32 s_warp_total[kEncThreads / 32];
   __shared__ u32 s_tile;
@@ -55,141 +74,134 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);
   for (unsigned s = t; s < GH_NSYM; s += kEncThreads) {
-    s_code[s] = table.codeword[s];
+    s_lut[s] = kSymsPerChunk == 4 ? ((u32(table.length[s]) << 16) | table.codeword[s]) : table.codeword[s];
     s_len[s] = table.length[s];
   }
+  for (unsigned i = t; i < unsigned(kEncStageWords); i += kEncThreads) s_stage[i] = 0;
   __syncthreads();
-  const u64 tile = s_tile;
   const u64 ntiles = enc_num_tiles(n);
-  const bool last_tile = (tile + 1 == ntiles);
+  const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
+  const u32 eof_len_all = table.length[GH_EOF_SYMBOL];
 
-  // ---- 1. load + gather --------------------------------------------------------------------------
-  const u64 base = tile * kEncTileBytes + u64(t) * kEncBytesPerThread;
-  u32 w[4] = {0, 0, 0, 0};
-  int cnt = 0;
-  if (base + kEncBytesPerThread <= n) {
-    const uint4 v = ldg128(reinterpret_cast<const uint4*>(in + base));
-    w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
-    cnt = kEncBytesPerThread;
-  } else if (base < n) {
-    cnt = int(n - base);
-    for (int k = 0; k < cnt; ++k) w[k >> 2] |= u32(in[base + k]) << (8 * (k & 3));
-  }
-  u32 code[kEncBytesPerThread];
-  u32 len[kEncBytesPerThread];
-  u32 my_bits = 0;
+  for (u64 tile = s_tile; tile < ntiles; tile = s_tile) {
+    const bool last_tile = (tile + 1 == ntiles);
+    // ---- 1. load + gather + concatenate in registers ---------------------------------------------------
+    const u64 base = tile * kEncTileBytes + u64(t) * kEncBytesPerThread;
+    u32 w[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    if (base + kEncBytesPerThread <= n) {
+      const uint4 v = ldg128(reinterpret_cast<const uint4*>(in + base));
+      w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+      cnt = kEncBytesPerThread;
+    } else if (base < n) {
+      cnt = int(n - base);
+      const uint4 v = load_ragged(in + base, cnt);
+      w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+    }
+    u64 chunk[kChunks];
+    u32 chunk_len[kChunks];
+    u32 my_bits = 0;
 #pragma unroll
-  for (int k = 0; k < kEncBytesPerThread; ++k) {
-    const u32 b = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
-    const bool live = k < cnt;
-    code[k] = s_code[b];
-    len[k] = live ? u32(s_len[b]) : 0u;
-    my_bits += len[k];
-  }
-  // the owner of the last byte also carries the end mark (its padding is only known after the scan)
-  const bool owns_end = append_eof && last_tile && (base < n) && (base + kEncBytesPerThread >= n);
-  const u32 eof_code = s_code[GH_EOF_SYMBOL];
-  const u32 eof_len = owns_end ? u32(s_len[GH_EOF_SYMBOL]) : 0u;
-  my_bits += eof_len;
-
-  // ---- 2. block scan + decoupled look-back -----------------------------------------------------------
-  const u32 incl = warp_inclusive_scan(my_bits, lane);
-  if (lane == 31) s_warp_total[warp] = incl;
-  __syncthreads();
-  u32 warp_base = 0, tile_bits = 0;
+    for (int c = 0; c < kChunks; ++c) {
+      u64 acc = 0;
+      u32 bits = 0;
 #pragma unroll
-  for (int k = 0; k < kEncThreads / 32; ++k) {
-    const u32 wt = s_warp_total[k];
-    if (unsigned(k) < warp) warp_base += wt;
-    tile_bits += wt;
-  }
-  const u32 excl = warp_base + incl - my_bits;  // bits of this tile before this thread
-
-  if (warp == 0) {
-    u64 exclusive = start_bit;
-    if (tile == 0) {
-      if (lane == 0) st_volatile_u64(ws.tile_state, kFlagPrefix | (start_bit + tile_bits));
-    } else {
-      if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
-      exclusive = 0;
-      long long look = (long long)tile - 1;
-      while (true) {
-        const long long idx = look - (long long)lane;
-        u64 st = kFlagPrefix;  // virtual tiles before tile 0 contribute nothing
-        if (idx >= 0) {
-          do {
-            st = ld_volatile_u64(ws.tile_state + idx);
-          } while ((st & kFlagMask) == 0);
+      for (int j = 0; j < kSymsPerChunk; ++j) {
+        const int k = c * kSymsPerChunk + j;
+        const u32 b = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+        u32 code, len;
+        if (kSymsPerChunk == 4) {
+          const u32 e = s_lut[b];
+          code = e & 0xffffu;
+          len = e >> 16;
+        } else {
+          code = s_lut[b];
+          len = s_len[b];
         }
-        const unsigned has_prefix = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
-        // lanes up to and including the nearest tile that already knows its prefix contribute
-        const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;  // has_prefix != 0 once idx < 0 is reached
-        u64 contrib = (has_prefix == 0 || lane <= first) ? (st & ~kFlagMask) : 0ull;
-        exclusive += warp_sum64(contrib);
-        if (has_prefix) break;
-        look -= 32;
+        if (cnt != kEncBytesPerThread && k >= cnt) len = 0, code = 0;  // ragged last vector
+        acc = (acc << len) | code;  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
+        bits += len;
       }
-      if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
+      chunk[c] = acc;
+      chunk_len[c] = bits;
+      my_bits += bits;
     }
-    if (lane == 0) s_tile_start = exclusive;
-  }
+    // the owner of the last byte also carries the end mark
+    const bool owns_end = append_eof && last_tile && (base < n) && (base + kEncBytesPerThread >= n);
+    const u32 eof_len = owns_end ? eof_len_all : 0u;
+    my_bits += eof_len;
 
-  // ---- 3. pack into the phase-aligned staging buffer ----------------------------------------------
-  // zero the words this tile can touch (tile_bits + padding + phase)
-  const u32 zero_words = (tile_bits + 31 + 7 + 31) / 32 + 1;
-  for (u32 i = t; i < zero_words && i < u32(kEncStageWords); i += kEncThreads) s_stage[i] = 0;
-  __syncthreads();
-  const u64 G = s_tile_start;
-  const u32 phase = u32(G & 31);
-  const u64 my_start = u64(phase) + excl;  // bit position inside the staging buffer
-  u32 wi = u32(my_start >> 5);
-  u32 fill = u32(my_start & 31);  // bits of word wi that belong to earlier threads (kept zero here)
-  u64 acc = 0;                    // bits [63 .. 64-fill) stay zero, ours follow
-  bool first_word = true;
-
-  auto put = [&](u32 c, u32 l) {
-    // l in 0..32, fill in 0..31 -> fill + l <= 63
-    if (l) acc |= u64(c) << (64 - fill - l);
-    fill += l;
-    if (fill >= 32) {
-      const u32 word = u32(acc >> 32);
-      if (first_word) {
-        atomicOr(&s_stage[wi], word);  // may share the word with the previous thread's tail
-        first_word = false;
-      } else {
-        s_stage[wi] = word;  // a word this thread filled from bit 31 down: exclusively ours
-      }
-      ++wi;
-      acc <<= 32;
-      fill -= 32;
-    }
-  };
+    // ---- 2. block scan; warp 0 resolves the global offset while the others pack ------------------------
+    const u32 incl = warp_inclusive_scan(my_bits, lane);
+    if (lane == 31) s_warp_total[warp] = incl;
+    __syncthreads();  // (a)
+    u32 warp_base = 0, tile_bits = 0;
 #pragma unroll
-  for (int k = 0; k < kEncBytesPerThread; ++k) put(code[k], len[k]);
-  u64 tile_bits_padded = tile_bits;
-  if (owns_end) {
-    put(eof_code, eof_len);
-    const u64 end_bit = G + excl + my_bits;  // first bit after the end mark
-    const u32 pad = u32((8 - (end_bit & 7)) & 7);
-    put((1u << pad) - 1u, pad);  // flush_bits(): fill the last byte with 1s (utils/include/buffer.h:277-280)
-    if (end_bit_out) *end_bit_out = end_bit;
-  }
-  if (fill) atomicOr(&s_stage[wi], u32(acc >> 32));
-  if (!append_eof && last_tile && t == 0 && end_bit_out) *end_bit_out = G + tile_bits;
-  if (append_eof && last_tile) {
-    const u64 end_bit = G + tile_bits;
-    tile_bits_padded += (8 - (end_bit & 7)) & 7;
-  }
-  __syncthreads();
+    for (int k = 0; k < kEncThreads / 32; ++k) {
+      const u32 wt = s_warp_total[k];
+      if (unsigned(k) < warp) warp_base += wt;
+      tile_bits += wt;
+    }
+    u32 pos = warp_base + incl - my_bits;  // tile-relative bit position of this thread's first bit
 
-  // ---- 4. store: one writer per output word ------------------------------------------------------------
-  const u64 word0 = G >> 5;
-  const u32 nwords = u32((u64(phase) + tile_bits_padded + 31) >> 5);
-  const bool shared_head = (tile > 0) && (phase != 0);
-  if (shared_head && t == 0) ws.head[tile] = s_stage[0];
-  for (u32 i = t + (shared_head ? 1u : 0u); i < nwords; i += kEncThreads) {
-    const u64 gw = word0 + i;
-    if (gw < out_word_cap) out_words[gw] = be32(s_stage[i]);
+    if (warp == 0) {
+      u64 exclusive = start_bit;
+      if (tile == 0) {
+        if (lane == 0) st_volatile_u64(ws.tile_state, kFlagPrefix | (start_bit + tile_bits));
+      } else {
+        if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
+        exclusive = 0;
+        long long look = (long long)tile - 1;
+        while (true) {
+          const long long idx = look - (long long)lane;
+          u64 st = kFlagPrefix;  // virtual tiles before tile 0 contribute nothing
+          if (idx >= 0) {
+            do {
+              st = ld_volatile_u64(ws.tile_state + idx);
+            } while ((st & kFlagMask) == 0);
+          }
+          const unsigned has_prefix = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
+          // lanes up to and including the nearest tile that already knows its prefix contribute
+          const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
+          const u64 contrib = (has_prefix == 0 || lane <= first) ? (st & ~kFlagMask) : 0ull;
+          exclusive += warp_sum64(contrib);
+          if (has_prefix) break;
+          look -= 32;
+        }
+        if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
+      }
+      if (lane == 0) s_tile_start = exclusive;
+    }
+
+    // ---- 3. pack at tile-relative positions -----------------------------------------------------------
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      if (chunk_len[c]) stage_bits(s_stage, pos, chunk[c], chunk_len[c]);
+      pos += chunk_len[c];
+    }
+    if (eof_len) stage_bits(s_stage, pos, eof_code, eof_len);
+    __syncthreads();  // (c) staging complete, s_tile_start written
+    if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);  // next tile for this block (read after barrier (d))
+
+    // ---- 4. copy-out with the phase shift; one writer per output word -----------------------------------
+    const u64 G = s_tile_start;
+    const u32 phase = u32(G & 31);
+    const u64 end_bit = G + tile_bits;  // first bit after this tile (after the end mark on the last tile)
+    u32 pad = 0;
+    if (append_eof && last_tile) pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s up to the byte boundary
+    if (last_tile && t == 0 && end_bit_out) *end_bit_out = end_bit;
+    const u64 word0 = G >> 5;
+    const u32 nwords = u32((u64(phase) + tile_bits + pad + 31) >> 5);
+    const bool shared_head = (tile > 0) && (phase != 0);
+    for (u32 i = t; i < nwords; i += kEncThreads) {
+      u32 v = __funnelshift_r(s_stage[i], i ? s_stage[i - 1] : 0u, phase);
+      const u64 gw = word0 + i;
+      if (pad && gw == (end_bit >> 5)) v |= ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad));
+      if (i == 0 && shared_head) ws.head[tile] = v;
+      else if (gw < out_word_cap) out_words[gw] = be32(v);
+    }
+    __syncthreads();  // (d) staged words consumed, s_tile updated
+    for (u32 i = t; i < (tile_bits >> 5) + 2; i += kEncThreads) s_stage[i] = 0;  // clean for the next tile
   }
 }
 
@@ -272,8 +284,15 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   GH_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, used, (cudaStream_t)stream));
 
   const u64 out_word_cap = payload_cap / 4;
-  GH_LAUNCH(encode_kernel, unsigned(ntiles), kEncThreads, 0, stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
-            reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
+  u64 blocks = u64(sm_count() > 0 ? sm_count() : 1) * kEncBlocksPerSm;
+  if (blocks > ntiles) blocks = ntiles;
+  if (code->max_len <= 16) {
+    GH_LAUNCH(encode_kernel<4>, unsigned(blocks), kEncThreads, 0, stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
+              reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
+  } else {
+    GH_LAUNCH(encode_kernel<2>, unsigned(blocks), kEncThreads, 0, stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
+              reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
+  }
   rc = check_launch();
   if (rc != GH_OK) return rc;
   if (ntiles > 1) {

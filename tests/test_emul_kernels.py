@@ -175,3 +175,34 @@ def test_emulated_staged_entry_points(emu, ctx, oracle):
     back = np.zeros(n, dtype=np.uint8)
     emu.check(emu.lib.gh_decode_staged(ctx, back.ctypes.data, n), "gh_decode_staged")
     assert back.tobytes() == data
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "zipf"])
+def test_emulated_decode_sync_rounds(emu, oracle, kind):
+    """larger payloads through gh_decode_sync/gh_decode_write: uniform bytes (8/9-bit code whose 9-bit end mark
+    shows up on every mis-phased path: paths must run through false end marks), a 1-bit-dominated code (15
+    codewords per table lookup) and Zipf; also reports how many synchronisation rounds were needed"""
+    import golden_huffman_b200 as gh
+    import golden_huffman_b200.workloads as W
+    n = 200000
+    if kind == "uniform":
+        data = W.uniform_np(n, seed=3)
+    elif kind == "zipf":
+        data = W.zipf_np(n, seed=3)
+    else:
+        rng = np.random.default_rng(3)
+        data = np.where(rng.random(n) < 0.97, 7, rng.integers(0, 40, n)).astype(np.uint8)
+    raw = data.tobytes()
+    rc, code = oracle.build_code(oracle.histogram(raw))
+    _, payload = oracle.encode_payload(raw, code)
+    pcode = gh.GhCode.from_buffer_copy(bytes(code))
+    buf = aligned(len(payload) + 16)
+    buf[:len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+    ws = aligned(emu.decode_workspace_bytes(len(payload)) + 256)
+    res = emu.decode_sync(buf.ctypes.data, len(payload), len(payload), pcode, 0, True, ws.ctypes.data, ws.size)
+    assert res.eof_found and res.n_symbols == n
+    assert res.rounds <= 64, f"{kind}: {res.rounds} rounds at {res.sub_bytes}-byte subsequences"
+    out = aligned(n + 16)
+    emu.decode_write(buf.ctypes.data, len(payload), len(payload), pcode, out.ctypes.data, n, ws.ctypes.data, ws.size)
+    assert out[:n].tobytes() == raw
+    print(kind, "rounds", res.rounds, "sub_bytes", res.sub_bytes)

@@ -192,7 +192,8 @@ def test_sharded_slices_on_one_gpu(codec, oracle):
         assert int(end_bit.item()) == phase + bits
         nbytes = (phase + bits + 7) // 8
         base = (start - phase) // 8
-        stream[base:base + nbytes] |= payload[:nbytes].cpu().numpy()  # boundary byte: OR of the two shards
+        lo = phase // 8  # bytes before the one holding start_bit are not this shard's (and are not written)
+        stream[base + lo:base + nbytes] |= payload[lo:nbytes].cpu().numpy()  # boundary byte: OR of the two shards
         start += bits
     assert (stream[:ref_payload.size] == ref_payload).all()
 

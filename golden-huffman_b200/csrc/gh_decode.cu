@@ -18,7 +18,8 @@
 //                    Round k makes subsequences 0..k exact whatever the data, so termination and exactness are
 //                    unconditional; codes that synchronise slowly (near-fixed-length ones) just take more rounds,
 //                    each touching fewer subsequences.
-//   K6   offsets   : first end mark on the true path truncates the counts; exclusive scan -> output offsets.
+//   K6   offsets   : the first end mark on the synchronised path truncates the counts (one thread walks that one
+//                    subsequence to count the symbols before it); exclusive scan -> output offsets.
 //   K7   write     : every thread re-decodes its subsequence from its now-exact entry, up to 3 codewords per
 //                    13-bit table lookup (long codes: left-justified first_code search, as the reference's Fast
 //                    decoder does), and stores symbols 16 at a time with 128-bit stores.
@@ -36,11 +37,12 @@ constexpr u32 kMinSubBytes = 128;
 constexpr u32 kMaxSubBytes = 1u << 27;
 
 // per-subsequence state, one 64-bit word so it is read and written atomically
-//   [31:0] count   [47:32] entry   [55:48] exit   [56] eof
+//   [31:0] count   [47:32] entry   [55:48] exit   [56] has_eof
 // A path is the codeword chain that starts at bit `entry` of the subsequence. It runs THROUGH end marks (a
 // mis-phased path meets bit patterns that look like the end mark all the time; stopping there would throw away
-// the exit it needs to synchronise): `eof` says the path contains an end mark, `count` is the number of symbols
-// before the first one (all symbols if there is none), `exit` is where the path leaves the subsequence.
+// the exit it needs to synchronise). `count` is the number of codewords on the path, end marks included, and a
+// second array holds how many of them are end marks: both are additive, so when a corrected path meets the
+// stored one the stored tail can always be reused. `exit` is where the path leaves the subsequence.
 __host__ __device__ inline u64 pack_state(u32 count, u32 entry, u32 exit, u32 eof) {
   return u64(count) | (u64(entry & 0xffffu) << 32) | (u64(exit & 0xffu) << 48) | (u64(eof & 1u) << 56);
 }
@@ -56,8 +58,10 @@ struct DecControl {  // device-resident, copied back to the host after each roun
   u32 exit_bit;
   u32 eof_found;
   u32 sub_bytes;
-  u32 unmerged;  // walks of the last round that never met the stored path
+  u32 exits_changed;  // subsequences whose exit moved in the last round
   u64 n_sub;
+  u32 eof_prefix;     // symbols before the first end mark inside subsequence eof_index
+  u32 pad_;
 };
 
 struct DecWorkspace {
@@ -67,6 +71,7 @@ struct DecWorkspace {
   const u32* lutW;             // [2^13]
   DecControl* ctl;
   u64* sub;        // [n_sub]
+  u32* neof;       // [n_sub]  end-mark codewords on each subsequence's path
   u64* tile_sum;   // [n_tiles]
   u64* tile_base;  // [n_tiles]
 };
@@ -186,19 +191,22 @@ struct BitReader {
   const uint8_t* bytes;
   u64 readable;
   u64 full_vecs;  // vectors that lie entirely inside the readable range
-  u64 vi;         // index of the NEXT vector to load
+  u64 vi;         // index of the vector held in `ahead`
+  uint4 ahead;    // the vector after the one being consumed, requested one vector early to cover the latency
   u32 w0, w1, w2, w3;  // upcoming 32-bit words (stream order), w0 first
   u32 left;            // how many of them are still unread (1..4)
   u64 buf;             // next `avail` stream bits, left-justified
   int avail;           // kept >= 32 between symbols
 
+  __device__ __forceinline__ uint4 fetch(u64 v) const {
+    if (v < full_vecs) return ldg128(reinterpret_cast<const uint4*>(bytes) + v);
+    return fetch_tail(bytes, readable, v);
+  }
   __device__ __forceinline__ void load_next() {
-    uint4 v;
-    if (vi < full_vecs) v = ldg128(reinterpret_cast<const uint4*>(bytes) + vi);
-    else v = fetch_tail(bytes, readable, vi);
-    ++vi;
-    w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+    w0 = ahead.x, w1 = ahead.y, w2 = ahead.z, w3 = ahead.w;
     left = 4;
+    ++vi;
+    ahead = fetch(vi);
   }
   __device__ __forceinline__ void push() {
     buf |= u64(be32(w0)) << (32 - avail);
@@ -211,6 +219,7 @@ struct BitReader {
     readable = readable_bytes;
     full_vecs = readable_bytes >> 4;
     vi = bitpos >> 7;
+    ahead = fetch(vi);
     load_next();
     const u32 skip = u32(bitpos >> 5) & 3u;  // words of this vector that lie before bitpos
     for (u32 k = 0; k < skip; ++k) w0 = w1, w1 = w2, w2 = w3;
@@ -260,46 +269,94 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
   const u64 start = i * u64(g.sub_bytes) * 8;
   const u32 end = u32(sub_end_bits(g, i));
   const u32 entry = (i == 0) ? g.entry0 : 0u;
-  u32 pos = entry, count = 0, eof = 0, count_at_eof = 0;
+  u32 pos = entry, count = 0, neof = 0;
+  const bool bulk = end >= u32(kLutCBits);
+  const u32 last = end - u32(kLutCBits);  // multi-codeword steps are allowed while pos <= last (only used if bulk)
+  // (a) bulk, word-synchronous: every lane pushes exactly one 32-bit word per step (statically indexed register of
+  //     the current 128-bit vector, next vector already requested), then takes table lookups while it holds >= 32
+  //     bits. The refill is unconditional straight-line code, so the only data-dependent control flow left in the
+  //     warp is the lookup loop itself. Nothing taken from the 15-bit table can cross `end`.
+  {
+    const u64 bit0 = start + pos;
+    u64 v = bit0 >> 7;
+    u32 k0 = u32(bit0 >> 5) & 3u;  // words of the first vector that lie before the start (subsequence 0 only)
+    u32 drop = u32(bit0) & 31u;
+    const u64 full_vecs = g.readable >> 4;
+    if (bulk && v + 1 < full_vecs) {
+      const uint4* vp = reinterpret_cast<const uint4*>(g.payload);
+      uint4 cur = ldg128(vp + v), nxt = ldg128(vp + v + 1);
+      u64 buf = 0;
+      int avail = 0;
+      bool more = true;
+      while (more) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (u32(k) < k0) continue;
+          const u32 w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
+          buf |= u64(be32(w)) << (32 - avail);
+          avail += 32;
+          if (drop) buf <<= drop, avail -= int(drop), drop = 0;
+          while (avail >= 32 && pos <= last) {
+            const u32 win = u32(buf >> 32);
+            const u32 e = s.lutC[win >> (32 - kLutCBits)];
+            u32 len;
+            if (e) {
+              len = e & 15u;
+              count += e >> 4;
+            } else {  // first codeword longer than 15 bits, or the end mark
+              u32 sym;
+              decode_one(s.canon, s.lut1, win, sym, len);
+              ++count;
+              neof += sym == u32(GH_EOF_SYMBOL);
+            }
+            pos += len;
+            buf <<= len;
+            avail -= int(len);
+          }
+          if (pos > last) {
+            more = false;
+            break;
+          }
+        }
+        k0 = 0;
+        if (!more) break;
+        ++v;
+        if (v + 1 >= full_vecs) break;  // the last vectors of the payload go through the bounds-checked reader
+        cur = nxt;
+        nxt = ldg128(vp + v + 1);
+      }
+    }
+  }
+  // (a') whatever the bulk loop left (payload tail), same steps through the bounds-checked reader
   BitReader r;
   r.seek(g.payload, g.readable, start + pos);
-  // (a) multi-codeword steps while a full 15-bit window lies inside the subsequence: nothing taken from the
-  //     table can cross `end`, so the first boundary at or after `end` is found exactly by (b)
-  if (end >= u32(kLutCBits)) {
-    const u32 last = end - u32(kLutCBits);
-    while (pos <= last) {
-      const u32 win = r.window();
-      const u32 e = s.lutC[win >> (32 - kLutCBits)];
-      u32 len;
-      if (e) {
-        len = e & 15u;
-        count += e >> 4;
-      } else {  // first codeword longer than 15 bits, or the end mark
-        u32 sym;
-        decode_one(s.canon, s.lut1, win, sym, len);
-        if (sym == u32(GH_EOF_SYMBOL)) {
-          if (!eof) eof = 1, count_at_eof = count;
-        } else {
-          ++count;
-        }
-      }
-      pos += len;
-      r.consume(len);
+  while (bulk && pos <= last) {
+    const u32 win = r.window();
+    const u32 e = s.lutC[win >> (32 - kLutCBits)];
+    u32 len;
+    if (e) {
+      len = e & 15u;
+      count += e >> 4;
+    } else {
+      u32 sym;
+      decode_one(s.canon, s.lut1, win, sym, len);
+      ++count;
+      neof += sym == u32(GH_EOF_SYMBOL);
     }
+    pos += len;
+    r.consume(len);
   }
   // (b) single codewords up to the crossing
   while (pos < end) {
     u32 sym, len;
     decode_one(s.canon, s.lut1, r.window(), sym, len);
-    if (sym == u32(GH_EOF_SYMBOL)) {
-      if (!eof) eof = 1, count_at_eof = count;
-    } else {
-      ++count;
-    }
+    ++count;
+    neof += sym == u32(GH_EOF_SYMBOL);
     pos += len;
     r.consume(len);
   }
-  ws.sub[i] = pack_state(eof ? count_at_eof : count, entry, pos - end, eof);
+  ws.sub[i] = pack_state(count, entry, pos - end, neof != 0);
+  ws.neof[i] = neof;
 }
 
 // ---- K5b: one synchronisation round ------------------------------------------------------------------------
@@ -324,63 +381,57 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
     want = (i == 0) ? g.entry0 : st_exit(ld_volatile_u64(ws.sub + i - 1));
     stale = want != st_entry(mine);
   }
-  bool merged = true;
+  bool merged = true, exit_moved = false;
   if (stale) {
     const u64 start = i * u64(g.sub_bytes) * 8;
     const u32 end = u32(sub_end_bits(g, i));
     // path A = the stored one (from st_entry(mine)), path B = the one we now believe in (from `want`).
     // Always step the one that is behind; where they meet, the rest of A's stored result is B's.
     u32 pos_a = st_entry(mine), pos_b = want;
-    u32 steps_a = 0, steps_b = 0, eof_b = 0, count_b_at_eof = 0;
-    bool a_usable = true;  // false once A has run through an end mark: its stored count stops there
+    u32 steps_a = 0, steps_b = 0, eofs_a = 0, eofs_b = 0;
     merged = false;
     BitReader ra, rb;
     ra.seek(g.payload, g.readable, start + pos_a);
     rb.seek(g.payload, g.readable, start + pos_b);
     while (pos_b < end) {
-      if (a_usable && pos_a == pos_b) {
+      if (pos_a == pos_b) {
         merged = true;
         break;
       }
       u32 sym, len;
-      if (a_usable && pos_a < pos_b) {
+      if (pos_a < pos_b) {
         decode_one(s.canon, s.lut1, ra.window(), sym, len);
-        if (sym == u32(GH_EOF_SYMBOL)) a_usable = false;
-        else ++steps_a;
+        ++steps_a;
+        eofs_a += sym == u32(GH_EOF_SYMBOL);
         pos_a += len;
         ra.consume(len);
       } else {
         decode_one(s.canon, s.lut1, rb.window(), sym, len);
-        if (sym == u32(GH_EOF_SYMBOL)) {
-          if (!eof_b) eof_b = 1, count_b_at_eof = steps_b;
-        } else {
-          ++steps_b;
-        }
+        ++steps_b;
+        eofs_b += sym == u32(GH_EOF_SYMBOL);
         pos_b += len;
         rb.consume(len);
       }
     }
-    u32 count, exit, eof;
-    if (merged) {
+    u32 count, exit, neof;
+    if (merged) {  // codeword and end-mark counts are additive: B's tail is A's tail
       exit = st_exit(mine);
-      if (eof_b) {
-        eof = 1, count = count_b_at_eof;
-      } else {  // A had no end mark before the meeting point, so its stored count/eof continue B's
-        eof = st_eof(mine);
-        count = steps_b + (st_count(mine) - steps_a);
-      }
+      count = steps_b + (st_count(mine) - steps_a);
+      neof = eofs_b + (ws.neof[i] - eofs_a);
     } else {
       exit = pos_b - end;
-      eof = eof_b;
-      count = eof_b ? count_b_at_eof : steps_b;
+      count = steps_b;
+      neof = eofs_b;
     }
-    st_volatile_u64(ws.sub + i, pack_state(count, want, exit, eof));
-    if (exit != st_exit(mine) || eof != st_eof(mine)) ws.ctl->changed = 1u;
+    ws.neof[i] = neof;
+    st_volatile_u64(ws.sub + i, pack_state(count, want, exit, neof != 0));
+    exit_moved = exit != st_exit(mine);
+    if (exit_moved) ws.ctl->changed = 1u;
   }
-  // how many walks ran to the end of their subsequence without meeting the stored path: the host uses the
-  // fraction after the first round to decide whether this code needs coarser subsequences
-  const unsigned lost = __ballot_sync(0xffffffffu, !merged);
-  if ((threadIdx.x & 31) == 0 && lost) atomicAdd(&ws.ctl->unmerged, u32(__popc(lost)));
+  // how many exits moved: after the first round the host uses the fraction to decide whether this code needs
+  // coarser subsequences (an exit that depends on the entry means the paths did not meet inside the subsequence)
+  const unsigned moved = __ballot_sync(0xffffffffu, exit_moved);
+  if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&ws.ctl->exits_changed, u32(__popc(moved)));
 }
 
 // ---- K6: truncate at the first end mark, turn counts into output offsets -----------------------------------
@@ -400,6 +451,33 @@ dec_tile_sum_kernel(DecGeometry g, DecWorkspace ws) {
   }
 }
 
+// The first subsequence (in stream order) whose synchronised path contains an end mark ends the stream; how many
+// symbols precede that mark is found by walking just that one subsequence. One thread; it is at most one
+// subsequence of work and for a well-formed stream the last, usually short, one.
+__global__ void __launch_bounds__(32)
+dec_locate_eof_kernel(DecGeometry g, DecWorkspace ws) {
+  __shared__ SmemCanon s;
+  load_canon(s, ws.tables);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const u32 i = ws.ctl->eof_index;
+  if (i == kNoEof) return;
+  const u64 st = ws.sub[i];
+  const u32 end = u32(sub_end_bits(g, i));
+  u32 pos = st_entry(st), count = 0;
+  BitReader r;
+  r.seek(g.payload, g.readable, u64(i) * u64(g.sub_bytes) * 8 + pos);
+  while (pos < end) {
+    u32 sym, len;
+    decode_one(s, ws.lut1, r.window(), sym, len);
+    if (sym == u32(GH_EOF_SYMBOL)) break;
+    ++count;
+    pos += len;
+    r.consume(len);
+  }
+  ws.ctl->eof_prefix = count;
+}
+
 constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads)
 dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
@@ -410,11 +488,12 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
   const u32 eof_index = ws.ctl->eof_index;
   const u64 eof_tile = eof_index == kNoEof ? n_tiles : u64(eof_index) / kDecThreads;
 
-  // the tile holding the end mark only counts subsequences up to and including that one
+  // the tile holding the first end mark: whole subsequences before it, then the symbols before the mark itself
   u64 part = 0;
   if (eof_index != kNoEof && t < unsigned(kDecThreads)) {
     const u64 i = eof_tile * kDecThreads + t;
-    if (i <= u64(eof_index)) part = st_count(ws.sub[i]);
+    if (i < u64(eof_index)) part = st_count(ws.sub[i]);
+    else if (i == u64(eof_index)) part = ws.ctl->eof_prefix;
   }
   part = warp_sum64(part);
   if (lane == 0) s_warp[warp] = part;
@@ -459,8 +538,8 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
 }
 
 // ---- K7: final decode from the exact entries ------------------------------------------------------------------
-// Up to 3 codewords per lookup (13-bit window); symbols are collected 8 at a time in a 64-bit register and two
-// such registers leave as one 128-bit store (16-byte aligned: the first few symbols go out as bytes).
+// Up to 3 codewords per lookup (13-bit window); symbols are collected 8 at a time in a 64-bit register and four
+// such registers leave as one full 32-byte sector (the first few symbols go out as bytes to reach alignment).
 struct SmemWrite {
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
@@ -483,7 +562,7 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   u32 count = 0;
   if (i < g.n_sub && i <= u64(eof_index)) {
     st = ws.sub[i];
-    count = st_count(st);
+    count = i == u64(eof_index) ? ws.ctl->eof_prefix : st_count(st);  // nothing is emitted past the end mark
   }
   const u32 incl = warp_inclusive_scan(count, lane);
   if (lane == 31) s.warp_total[warp] = incl;
@@ -497,23 +576,109 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   u64 remaining = count;
   if (remaining > out_cap - o) remaining = out_cap - o;
 
-  BitReader r;
-  r.seek(g.payload, g.readable, i * u64(g.sub_bytes) * 8 + st_entry(st));
+  const u64 start = i * u64(g.sub_bytes) * 8;
+  u32 pos = st_entry(st);  // bits of the subsequence consumed so far
   uint8_t* dst = out + o;
   u32 sym, len;
-  // head: single symbols up to the first 16-byte boundary of the output
-  while (remaining && (reinterpret_cast<uintptr_t>(dst) & 15)) {
-    decode_one(s.canon, s.lut1, r.window(), sym, len);
-    r.consume(len);
-    *dst++ = uint8_t(sym);
-    --remaining;
+  // head: single symbols up to the first 32-byte boundary of the output
+  {
+    BitReader r;
+    r.seek(g.payload, g.readable, start + pos);
+    while (remaining && (reinterpret_cast<uintptr_t>(dst) & 31)) {
+      decode_one(s.canon, s.lut1, r.window(), sym, len);
+      r.consume(len);
+      pos += len;
+      *dst++ = uint8_t(sym);
+      --remaining;
+    }
   }
-  // body: `acc` collects symbols (first symbol in the lowest byte); every 8 symbols it is retired, every second
-  // retirement is a 128-bit store
-  u64 acc = 0, held = 0;
-  u32 nacc = 0;      // symbols in acc (0..7 between steps)
-  bool have_held = false;
-  while (remaining >= u64(kLutWMaxSyms)) {  // any table entry yields at most kLutWMaxSyms symbols
+  // body: `acc` collects symbols (first symbol in the lowest byte); every 8 symbols it is retired into
+  // held[0..2], and the fourth retirement writes one whole 32-byte sector as two back-to-back 128-bit stores
+  // (lanes write to scattered places, so anything narrower leaves L2 with partially written sectors).
+  // The bit stream side is word-synchronous as in K5a: one unconditional 32-bit push per step from a statically
+  // indexed register, then table lookups while >= 32 bits are held.
+  u64 acc = 0, held0 = 0, held1 = 0, held2 = 0;
+  u32 nacc = 0;   // symbols in acc (0..7 between steps)
+  u32 nheld = 0;  // retired 8-symbol groups waiting in held0..2
+  auto emit = [&](u32 syms, u32 n) {
+    const u32 sh = nacc * 8;
+    acc |= u64(syms) << sh;
+    nacc += n;
+    if (nacc >= 8) {
+      const u64 spill = sh > 40 ? u64(syms) >> (64 - sh) : 0ull;  // bytes that did not fit
+      if (nheld == 3) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        d4[0] = make_uint4(u32(held0), u32(held0 >> 32), u32(held1), u32(held1 >> 32));
+        d4[1] = make_uint4(u32(held2), u32(held2 >> 32), u32(acc), u32(acc >> 32));
+        dst += 32;
+        nheld = 0;
+      } else {
+        if (nheld == 0) held0 = acc;
+        else if (nheld == 1) held1 = acc;
+        else held2 = acc;
+        ++nheld;
+      }
+      acc = spill;
+      nacc -= 8;
+    }
+  };
+  {
+    const u64 bit0 = start + pos;
+    u64 v = bit0 >> 7;
+    u32 k0 = u32(bit0 >> 5) & 3u;
+    u32 drop = u32(bit0) & 31u;
+    const u64 full_vecs = g.readable >> 4;
+    if (remaining >= u64(kLutWMaxSyms) && v + 1 < full_vecs) {
+      const uint4* vp = reinterpret_cast<const uint4*>(g.payload);
+      uint4 cur = ldg128(vp + v), nxt = ldg128(vp + v + 1);
+      u64 buf = 0;
+      int avail = 0;
+      bool more = true;
+      while (more) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (u32(k) < k0) continue;
+          const u32 w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
+          buf |= u64(be32(w)) << (32 - avail);
+          avail += 32;
+          if (drop) buf <<= drop, avail -= int(drop), drop = 0;
+          while (avail >= 32 && remaining >= u64(kLutWMaxSyms)) {  // an entry yields at most kLutWMaxSyms symbols
+            const u32 win = u32(buf >> 32);
+            const u32 e = s.lutW[win >> (32 - kLutWBits)];
+            u32 n, syms;
+            if (e) {
+              len = e & 15u;
+              n = (e >> 4) & 3u;
+              syms = e >> 8;
+            } else {  // codeword longer than 13 bits (the end mark cannot occur: the count stops before it)
+              decode_one(s.canon, s.lut1, win, sym, len);
+              n = 1;
+              syms = sym & 0xffu;
+            }
+            pos += len;
+            buf <<= len;
+            avail -= int(len);
+            remaining -= n;
+            emit(syms, n);
+          }
+          if (remaining < u64(kLutWMaxSyms)) {
+            more = false;
+            break;
+          }
+        }
+        k0 = 0;
+        if (!more) break;
+        ++v;
+        if (v + 1 >= full_vecs) break;
+        cur = nxt;
+        nxt = ldg128(vp + v + 1);
+      }
+    }
+  }
+  // what the bulk loop left (payload tail or the last couple of symbols): bounds-checked reader from `pos`
+  BitReader r;
+  r.seek(g.payload, g.readable, start + pos);
+  while (remaining >= u64(kLutWMaxSyms)) {
     const u32 win = r.window();
     const u32 e = s.lutW[win >> (32 - kLutWBits)];
     u32 n, syms;
@@ -521,35 +686,19 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
       len = e & 15u;
       n = (e >> 4) & 3u;
       syms = e >> 8;
-    } else {  // codeword longer than 13 bits (the end mark cannot occur: the count stops before it)
+    } else {
       decode_one(s.canon, s.lut1, win, sym, len);
       n = 1;
       syms = sym & 0xffu;
     }
     r.consume(len);
     remaining -= n;
-    const u32 sh = nacc * 8;
-    acc |= u64(syms) << sh;
-    nacc += n;
-    if (nacc >= 8) {
-      const u64 spill = sh > 40 ? u64(syms) >> (64 - sh) : 0ull;  // bytes that did not fit
-      if (have_held) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(u32(held), u32(held >> 32), u32(acc), u32(acc >> 32));
-        dst += 16;
-        have_held = false;
-      } else {
-        held = acc;
-        have_held = true;
-      }
-      acc = spill;
-      nacc -= 8;
-    }
+    emit(syms, n);
   }
   // drain what is collected, then the last few symbols one by one
-  if (have_held) {
-    *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held), u32(held >> 32));
-    dst += 8;
-  }
+  if (nheld > 0) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held0), u32(held0 >> 32)), dst += 8;
+  if (nheld > 1) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held1), u32(held1 >> 32)), dst += 8;
+  if (nheld > 2) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held2), u32(held2 >> 32)), dst += 8;
   for (u32 k = 0; k < nacc; ++k) *dst++ = uint8_t(acc >> (8 * k));
   while (remaining) {
     decode_one(s.canon, s.lut1, r.window(), sym, len);
@@ -561,7 +710,7 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
 
 // ---- host orchestration -------------------------------------------------------------------------------
 struct DecLayout {
-  size_t off_tables, off_lut1, off_lutC, off_lutW, off_ctl, off_sub, off_tile_sum, off_tile_base, total;
+  size_t off_tables, off_lut1, off_lutC, off_lutW, off_ctl, off_sub, off_neof, off_tile_sum, off_tile_base, total;
 };
 
 static DecLayout dec_layout(u64 slice_bytes) {
@@ -575,7 +724,8 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_lutW = L.off_lutC + up(sizeof(uint8_t) << kLutCBits);
   L.off_ctl = L.off_lutW + up(sizeof(u32) << kLutWBits);
   L.off_sub = L.off_ctl + 256;
-  L.off_tile_sum = L.off_sub + up(size_t(max_sub) * 8);
+  L.off_neof = L.off_sub + up(size_t(max_sub) * 8);
+  L.off_tile_sum = L.off_neof + up(size_t(max_sub) * 4);
   L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
   L.total = L.off_tile_base + up(size_t(max_tiles) * 8);
   return L;
@@ -590,6 +740,7 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   w.lutW = reinterpret_cast<const u32*>(p + L.off_lutW);
   w.ctl = reinterpret_cast<DecControl*>(p + L.off_ctl);
   w.sub = reinterpret_cast<u64*>(p + L.off_sub);
+  w.neof = reinterpret_cast<u32*>(p + L.off_neof);
   w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
   w.tile_base = reinterpret_cast<u64*>(p + L.off_tile_base);
   return w;
@@ -607,6 +758,7 @@ static u32 choose_sub_bytes(u64 slice_bytes) {
 static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream) {
   const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
   GH_LAUNCH(dec_tile_sum_kernel, tiles, kDecThreads, 0, stream, g, ws);
+  GH_LAUNCH(dec_locate_eof_kernel, 1, 32, 0, stream, g, ws);
   GH_LAUNCH(dec_offsets_kernel, 1, kScanThreads, 0, stream, g, ws);
   int rc = check_launch();
   if (rc != GH_OK) return rc;
@@ -640,6 +792,9 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     GH_LAUNCH(dec_build_luts_kernel, (1u << kLutCBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
               const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW));
     g.sub_bytes = choose_sub_bytes(slice_bytes);
+    // near-fixed-length codes (all lengths within one bit: uniform-looking bytes) re-synchronise only when one of
+    // the rare longer codewords shifts the phase; start them 4x coarser instead of finding that out the hard way
+    if (code->max_len - code->min_len <= 1 && u64(g.sub_bytes) * 4 <= kMaxSubBytes) g.sub_bytes *= 4;
   } else {
     GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
     GH_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -649,9 +804,10 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   // Synchronisation rounds until a clean one. Round k makes subsequences 0..k exact whatever the data, so this
   // terminates after at most n_sub rounds; with codes that self-synchronise it takes two or three.
   // A code that synchronises slowly relative to the subsequence size (near-fixed-length codes: uniform bytes)
-  // shows up in the first round as many walks that never meet the stored path; the expected number of rounds is
-  // then log(n_sub) / log(1 / that fraction), so the subsequences are made 4x coarser (fraction -> fraction^4)
-  // and the speculation is redone -- one extra pass instead of dozens of rounds.
+  // shows up in the first round as many exits that move (the corrected path never met the speculated one inside
+  // the subsequence); the expected number of rounds is then log(n_sub) / log(1 / that fraction), so the
+  // subsequences are made 4x coarser (fraction -> fraction^4) and the speculation is redone -- one extra pass
+  // instead of dozens of rounds.
   u32 rounds = 0;
   bool speculate = first_call != 0;
   while (true) {
@@ -676,7 +832,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
       GH_CUDA_TRY(cudaStreamSynchronize(stream));
       ++rounds;
       if (!h_ctl.changed) break;
-      if (level_round == 0 && speculate && g.n_sub >= 64 && u64(h_ctl.unmerged) * 16 > g.n_sub &&
+      if (level_round == 0 && speculate && g.n_sub >= 64 && u64(h_ctl.exits_changed) * 16 > g.n_sub &&
           g.sub_bytes < kMaxSubBytes) {
         coarsen = true;
         break;

@@ -14,7 +14,7 @@ namespace gh {
 
 constexpr int kHistThreads = 224;
 constexpr int kHistSmemBytes = 256 * kHistThreads * 4;
-constexpr int kHistUnroll = 4;
+constexpr int kHistUnroll = 8;  // 128-bit loads in flight per thread (x2: the next batch is requested before this one is consumed)
 
 __device__ __forceinline__ void hist_add_word(u32* col, u32 w) {
   atomicAdd(col + (w & 0xffu) * kHistThreads, 1u);
@@ -52,13 +52,27 @@ hist_kernel(const uint8_t* __restrict__ in, u64 n, u64* __restrict__ hist) {
   const uint4* vec = reinterpret_cast<const uint4*>(in + head);
   const u64 stride = u64(gridDim.x) * kHistThreads;
   u64 i = u64(blockIdx.x) * kHistThreads + t;
-  // kHistUnroll independent 128-bit loads in flight per thread before any is consumed
-  for (; i + (kHistUnroll - 1) * stride < nvec; i += kHistUnroll * stride) {
-    uint4 v[kHistUnroll];
+  // Software pipeline: batch k+1 is requested before batch k is consumed, so every thread keeps kHistUnroll to
+  // 2*kHistUnroll 128-bit loads outstanding. With one 224-thread CTA per SM the bytes in flight are what bounds
+  // the kernel (Little's law: ~45 KB per SM are needed to cover HBM latency at full bandwidth).
+  const u64 batch = u64(kHistUnroll) * stride;
+  if (i + (kHistUnroll - 1) * stride < nvec) {
+    uint4 cur[kHistUnroll];
 #pragma unroll
-    for (int k = 0; k < kHistUnroll; ++k) v[k] = ldg128(vec + i + k * stride);
+    for (int k = 0; k < kHistUnroll; ++k) cur[k] = ldg128(vec + i + k * stride);
+    i += batch;
+    while (i + (kHistUnroll - 1) * stride < nvec) {
+      uint4 nxt[kHistUnroll];
 #pragma unroll
-    for (int k = 0; k < kHistUnroll; ++k) hist_add_vec(col, v[k]);
+      for (int k = 0; k < kHistUnroll; ++k) nxt[k] = ldg128(vec + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < kHistUnroll; ++k) hist_add_vec(col, cur[k]);
+#pragma unroll
+      for (int k = 0; k < kHistUnroll; ++k) cur[k] = nxt[k];
+      i += batch;
+    }
+#pragma unroll
+    for (int k = 0; k < kHistUnroll; ++k) hist_add_vec(col, cur[k]);
   }
   for (; i < nvec; i += stride) hist_add_vec(col, ldg128(vec + i));
 

@@ -206,3 +206,21 @@ def test_emulated_decode_sync_rounds(emu, oracle, kind):
     emu.decode_write(buf.ctypes.data, len(payload), len(payload), pcode, out.ctypes.data, n, ws.ctypes.data, ws.size)
     assert out[:n].tobytes() == raw
     print(kind, "rounds", res.rounds, "sub_bytes", res.sub_bytes)
+
+
+def test_emulated_histogram_pipelined_path(emu, oracle):
+    """large enough for the software-pipelined main loop of K1 (several batches per thread), misaligned start,
+    plus the accumulate flag"""
+    rng = np.random.default_rng(11)
+    n = 400003
+    raw = aligned(n + 64)
+    raw[:] = rng.integers(0, 256, n + 64, dtype=np.uint8)
+    for off in (0, 3, 16):
+        view = raw[off:off + n]
+        hist = aligned(256, np.uint64)
+        emu.histogram(view.ctypes.data, n, hist.ctypes.data)
+        assert (hist == oracle.histogram(view.tobytes())).all()
+    hist = aligned(256, np.uint64)
+    emu.histogram(raw.ctypes.data, 1000, hist.ctypes.data)
+    emu.histogram(raw.ctypes.data + 1000, n - 1000, hist.ctypes.data, accumulate=True)
+    assert (hist == oracle.histogram(raw[:n].tobytes())).all()

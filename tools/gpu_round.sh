@@ -14,7 +14,7 @@ echo "smoke exit $?" | tee -a $OUT/${TAG}_smoke.log
 
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
   echo "== pytest -m gpu"
-  timeout 1500 python -m pytest tests -m gpu -x -q --timeout 600 > $OUT/${TAG}_pytest.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -x -q --timeout 600 ${PYTEST_ARGS:-} > $OUT/${TAG}_pytest.log 2>&1
   echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
   tail -15 $OUT/${TAG}_pytest.log
 fi
@@ -32,7 +32,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
   echo "ncu launches exit $?"
   echo "== ncu full"
-  $CMD > $OUT/${TAG}_ncu_plain2.log 2>&1 &&
+  [ "${SKIP_NCU_FULL:-0}" != "1" ] && $CMD > $OUT/${TAG}_ncu_plain2.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"hist_kernel|encode_kernel|dec_speculate_kernel|dec_sync_kernel|dec_write_kernel" -s ${NCU_SKIP:-24} -c ${NCU_COUNT:-8} -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
   echo "ncu full exit $?"
 fi

@@ -33,6 +33,7 @@ namespace gh {
 
 constexpr int kDecThreads = 256;   // threads per block = subsequences per tile, all decode kernels
 constexpr u32 kNoEof = 0xffffffffu;
+constexpr u32 kEofPosUnknown = 0xfffffffeu;
 constexpr u32 kMinSubBytes = 128;
 constexpr u32 kMaxSubBytes = 1u << 27;
 
@@ -72,6 +73,7 @@ struct DecWorkspace {
   DecControl* ctl;
   u64* sub;        // [n_sub]
   u32* neof;       // [n_sub]  end-mark codewords on each subsequence's path
+  u32* eofpos;     // [n_sub]  symbols before the path's first end mark, kEofPosUnknown if it was not observed
   u64* tile_sum;   // [n_tiles]
   u64* tile_base;  // [n_tiles]
 };
@@ -269,7 +271,7 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
   const u64 start = i * u64(g.sub_bytes) * 8;
   const u32 end = u32(sub_end_bits(g, i));
   const u32 entry = (i == 0) ? g.entry0 : 0u;
-  u32 pos = entry, count = 0, neof = 0;
+  u32 pos = entry, count = 0, neof = 0, first_eof = kNoEof;
   const bool bulk = end >= u32(kLutCBits);
   const u32 last = end - u32(kLutCBits);  // multi-codeword steps are allowed while pos <= last (only used if bulk)
   // (a) bulk, word-synchronous: every lane pushes exactly one 32-bit word per step (statically indexed register of
@@ -306,8 +308,11 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
             } else {  // first codeword longer than 15 bits, or the end mark
               u32 sym;
               decode_one(s.canon, s.lut1, win, sym, len);
+              if (sym == u32(GH_EOF_SYMBOL)) {
+                if (!neof) first_eof = count;
+                ++neof;
+              }
               ++count;
-              neof += sym == u32(GH_EOF_SYMBOL);
             }
             pos += len;
             buf <<= len;
@@ -340,8 +345,11 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
     } else {
       u32 sym;
       decode_one(s.canon, s.lut1, win, sym, len);
+      if (sym == u32(GH_EOF_SYMBOL)) {
+        if (!neof) first_eof = count;
+        ++neof;
+      }
       ++count;
-      neof += sym == u32(GH_EOF_SYMBOL);
     }
     pos += len;
     r.consume(len);
@@ -350,13 +358,17 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
   while (pos < end) {
     u32 sym, len;
     decode_one(s.canon, s.lut1, r.window(), sym, len);
+    if (sym == u32(GH_EOF_SYMBOL)) {
+      if (!neof) first_eof = count;
+      ++neof;
+    }
     ++count;
-    neof += sym == u32(GH_EOF_SYMBOL);
     pos += len;
     r.consume(len);
   }
   ws.sub[i] = pack_state(count, entry, pos - end, neof != 0);
   ws.neof[i] = neof;
+  ws.eofpos[i] = first_eof;  // codewords before the first end mark are all symbols
 }
 
 // ---- K5b: one synchronisation round ------------------------------------------------------------------------
@@ -388,7 +400,7 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
     // path A = the stored one (from st_entry(mine)), path B = the one we now believe in (from `want`).
     // Always step the one that is behind; where they meet, the rest of A's stored result is B's.
     u32 pos_a = st_entry(mine), pos_b = want;
-    u32 steps_a = 0, steps_b = 0, eofs_a = 0, eofs_b = 0;
+    u32 steps_a = 0, steps_b = 0, eofs_a = 0, eofs_b = 0, first_b = kNoEof;
     merged = false;
     BitReader ra, rb;
     ra.seek(g.payload, g.readable, start + pos_a);
@@ -407,23 +419,33 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
         ra.consume(len);
       } else {
         decode_one(s.canon, s.lut1, rb.window(), sym, len);
+        if (sym == u32(GH_EOF_SYMBOL)) {
+          if (!eofs_b) first_b = steps_b;
+          ++eofs_b;
+        }
         ++steps_b;
-        eofs_b += sym == u32(GH_EOF_SYMBOL);
         pos_b += len;
         rb.consume(len);
       }
     }
-    u32 count, exit, neof;
+    u32 count, exit, neof, first = first_b;
     if (merged) {  // codeword and end-mark counts are additive: B's tail is A's tail
       exit = st_exit(mine);
       count = steps_b + (st_count(mine) - steps_a);
-      neof = eofs_b + (ws.neof[i] - eofs_a);
+      const u32 tail_eofs = ws.neof[i] - eofs_a;
+      neof = eofs_b + tail_eofs;
+      if (!eofs_b && tail_eofs) {
+        // the first end mark lies in A's tail: known only if it is also A's first and A had observed it
+        const u32 a_first = ws.eofpos[i];
+        first = (eofs_a == 0 && a_first < kEofPosUnknown) ? steps_b + (a_first - steps_a) : kEofPosUnknown;
+      }
     } else {
       exit = pos_b - end;
       count = steps_b;
       neof = eofs_b;
     }
     ws.neof[i] = neof;
+    ws.eofpos[i] = first;
     st_volatile_u64(ws.sub + i, pack_state(count, want, exit, neof != 0));
     exit_moved = exit != st_exit(mine);
     if (exit_moved) ws.ctl->changed = 1u;
@@ -451,27 +473,45 @@ dec_tile_sum_kernel(DecGeometry g, DecWorkspace ws) {
   }
 }
 
-// The first subsequence (in stream order) whose synchronised path contains an end mark ends the stream; how many
-// symbols precede that mark is found by walking just that one subsequence. One thread; it is at most one
-// subsequence of work and for a well-formed stream the last, usually short, one.
-__global__ void __launch_bounds__(32)
+// The first subsequence (in stream order) whose synchronised path contains an end mark ends the stream. The number
+// of symbols before that mark is normally already known (eofpos, kept by the walks above); when the mark lay in a
+// reused tail whose own first end mark was a false one, that one subsequence is walked again by a single thread
+// (tables staged in shared memory by the whole block, 15-bit multi-codeword steps).
+__global__ void __launch_bounds__(kDecThreads)
 dec_locate_eof_kernel(DecGeometry g, DecWorkspace ws) {
-  __shared__ SmemCanon s;
-  load_canon(s, ws.tables);
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+  __shared__ SmemSpeculate s;
   const u32 i = ws.ctl->eof_index;
   if (i == kNoEof) return;
+  const u32 known = ws.eofpos[i];
+  if (known < kEofPosUnknown) {
+    if (threadIdx.x == 0) ws.ctl->eof_prefix = known;
+    return;
+  }
+  load_canon(s.canon, ws.tables);
+  for (unsigned k = threadIdx.x; k < (1u << kLut1Bits) / 2; k += kDecThreads)
+    reinterpret_cast<u32*>(s.lut1)[k] = reinterpret_cast<const u32*>(ws.lut1)[k];
+  for (unsigned k = threadIdx.x; k < (1u << kLutCBits) / 16; k += kDecThreads)
+    reinterpret_cast<uint4*>(s.lutC)[k] = reinterpret_cast<const uint4*>(ws.lutC)[k];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   const u64 st = ws.sub[i];
   const u32 end = u32(sub_end_bits(g, i));
   u32 pos = st_entry(st), count = 0;
   BitReader r;
   r.seek(g.payload, g.readable, u64(i) * u64(g.sub_bytes) * 8 + pos);
   while (pos < end) {
-    u32 sym, len;
-    decode_one(s, ws.lut1, r.window(), sym, len);
-    if (sym == u32(GH_EOF_SYMBOL)) break;
-    ++count;
+    const u32 win = r.window();
+    const u32 e = s.lutC[win >> (32 - kLutCBits)];
+    u32 len;
+    if (e) {  // whole codewords, never the end mark
+      len = e & 15u;
+      count += e >> 4;
+    } else {
+      u32 sym;
+      decode_one(s.canon, s.lut1, win, sym, len);
+      if (sym == u32(GH_EOF_SYMBOL)) break;
+      ++count;
+    }
     pos += len;
     r.consume(len);
   }
@@ -710,7 +750,7 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
 
 // ---- host orchestration -------------------------------------------------------------------------------
 struct DecLayout {
-  size_t off_tables, off_lut1, off_lutC, off_lutW, off_ctl, off_sub, off_neof, off_tile_sum, off_tile_base, total;
+  size_t off_tables, off_lut1, off_lutC, off_lutW, off_ctl, off_sub, off_neof, off_eofpos, off_tile_sum, off_tile_base, total;
 };
 
 static DecLayout dec_layout(u64 slice_bytes) {
@@ -725,7 +765,8 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_ctl = L.off_lutW + up(sizeof(u32) << kLutWBits);
   L.off_sub = L.off_ctl + 256;
   L.off_neof = L.off_sub + up(size_t(max_sub) * 8);
-  L.off_tile_sum = L.off_neof + up(size_t(max_sub) * 4);
+  L.off_eofpos = L.off_neof + up(size_t(max_sub) * 4);
+  L.off_tile_sum = L.off_eofpos + up(size_t(max_sub) * 4);
   L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
   L.total = L.off_tile_base + up(size_t(max_tiles) * 8);
   return L;
@@ -741,6 +782,7 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   w.ctl = reinterpret_cast<DecControl*>(p + L.off_ctl);
   w.sub = reinterpret_cast<u64*>(p + L.off_sub);
   w.neof = reinterpret_cast<u32*>(p + L.off_neof);
+  w.eofpos = reinterpret_cast<u32*>(p + L.off_eofpos);
   w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
   w.tile_base = reinterpret_cast<u64*>(p + L.off_tile_base);
   return w;
@@ -758,7 +800,7 @@ static u32 choose_sub_bytes(u64 slice_bytes) {
 static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream) {
   const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
   GH_LAUNCH(dec_tile_sum_kernel, tiles, kDecThreads, 0, stream, g, ws);
-  GH_LAUNCH(dec_locate_eof_kernel, 1, 32, 0, stream, g, ws);
+  GH_LAUNCH(dec_locate_eof_kernel, 1, kDecThreads, 0, stream, g, ws);
   GH_LAUNCH(dec_offsets_kernel, 1, kScanThreads, 0, stream, g, ws);
   int rc = check_launch();
   if (rc != GH_OK) return rc;
@@ -793,8 +835,8 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
               const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW));
     g.sub_bytes = choose_sub_bytes(slice_bytes);
     // near-fixed-length codes (all lengths within one bit: uniform-looking bytes) re-synchronise only when one of
-    // the rare longer codewords shifts the phase; start them 4x coarser instead of finding that out the hard way
-    if (code->max_len - code->min_len <= 1 && u64(g.sub_bytes) * 4 <= kMaxSubBytes) g.sub_bytes *= 4;
+    // the rare longer codewords shifts the phase; start them 2x coarser (rounds cost one subsequence walk each)
+    if (code->max_len - code->min_len <= 1 && u64(g.sub_bytes) * 2 <= kMaxSubBytes) g.sub_bytes *= 2;
   } else {
     GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
     GH_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -809,7 +851,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   // subsequences are made 4x coarser (fraction -> fraction^4) and the speculation is redone -- one extra pass
   // instead of dozens of rounds.
   u32 rounds = 0;
-  bool speculate = first_call != 0;
+  bool speculate = first_call != 0, coarsened = false;
   while (true) {
     g.n_sub = (slice_bytes + g.sub_bytes - 1) / g.sub_bytes;
     const unsigned blocks = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
@@ -832,14 +874,17 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
       GH_CUDA_TRY(cudaStreamSynchronize(stream));
       ++rounds;
       if (!h_ctl.changed) break;
-      if (level_round == 0 && speculate && g.n_sub >= 64 && u64(h_ctl.exits_changed) * 16 > g.n_sub &&
-          g.sub_bytes < kMaxSubBytes) {
+      // coarsen (once, and only while the grid still fills the GPU) when more than half of the exits moved in
+      // the first round: ~log(n_sub)/log(1/fraction) rounds are ahead, and a round costs one subsequence walk
+      if (level_round == 0 && speculate && !coarsened && u64(h_ctl.exits_changed) * 2 > g.n_sub &&
+          g.n_sub / 4 >= u64(sm_count()) * 512 && u64(g.sub_bytes) * 4 <= kMaxSubBytes) {
         coarsen = true;
         break;
       }
       if (u64(level_round) > g.n_sub + 2) return GH_ERR_FORMAT;  // cannot happen: see above
     }
     if (!coarsen) break;
+    coarsened = true;
     u64 bigger = u64(g.sub_bytes) * 4;
     g.sub_bytes = u32(bigger > kMaxSubBytes ? kMaxSubBytes : bigger);
     speculate = true;

@@ -5,31 +5,36 @@
 // Algorithmic traffic: N bytes read + C bytes written (the scan is fused by decoupled look-back, so the
 // input is not read a second time to learn the bit offsets).
 //
-// Persistent blocks take tiles of kEncThreads x 16 input bytes from an atomic ticket. Per tile:
-//   1. every thread loads one 128-bit vector (coalesced), gathers (codeword, length) for its 16 bytes from the
-//      shared-memory LUT and concatenates them in registers into 64-bit chunks (4 codewords per chunk when
-//      no code is longer than 16 bits, 2 otherwise) -- `acc = (acc << len) | code`, three instructions a symbol;
-//   2. the per-thread bit counts are scanned across the block (warp shuffles); warp 0 publishes the tile total
-//      and resolves the tile's global bit offset G by a warp-wide decoupled look-back over the predecessors'
-//      (flag | value) words WHILE the other warps already pack: packing only needs tile-relative offsets;
-//   3. each chunk is left-justified and OR-ed into a zeroed shared staging buffer at its tile-relative bit
-//      position (shared-memory atomics: neighbouring chunks share words);
-//   4. copy-out: global word (G/32 + i) = funnel-shift of staged words i-1, i by (G mod 32) -- the phase
-//      alignment with the output costs one SHF per output word -- byte-swapped to stream order, coalesced.
-//      The tile's first word, when shared with the previous tile, is NOT stored: its bits go to head[tile] and
-//      a tiny second kernel ORs them into the word the previous tile wrote -- every output word has exactly
-//      one writer per kernel, no global atomics on the payload. The last tile adds the end-mark codeword and
-//      the 1-padding (reference include/canonical_huff_encoder.cc:255-257).
+// Persistent blocks take tiles of kEncSubTiles x 4 KiB of input from an atomic ticket. Per tile:
+//   1. every thread issues kEncSubTiles coalesced 128-bit loads up front (one 16-byte vector per 4 KiB sub-tile,
+//      kept in registers) and sums the code lengths of its bytes from the shared-memory LUT;
+//   2. the per-thread bit counts are scanned per sub-tile (warp shuffles + one barrier); warp 0 publishes the
+//      tile total and resolves the tile's global bit offset G by a warp-wide decoupled look-back over the
+//      predecessors' (flag | value) words. One look-back per 16 KiB: the prefix can only travel 32 tiles per
+//      L2 round trip, so with 4 KiB tiles that chain, not the SMs, set the pace (measured: profiles/r1b);
+//   3. sub-tile by sub-tile: codewords are concatenated in registers into 64-bit chunks (4 per chunk when no
+//      code is longer than 16 bits, else 2) -- `acc = (acc << len) | code` -- and OR-ed into a zeroed shared
+//      staging buffer at sub-tile-relative bit positions (shared-memory atomics: neighbours share words).
+//      Packing needs no global offset, so the other warps pack while warp 0 is still looking back;
+//   4. copy-out: global word (G'/32 + i) = funnel-shift of staged words i-1, i by (G' mod 32), G' the sub-tile's
+//      global bit offset -- phase alignment costs one SHF per output word -- byte-swapped to stream order,
+//      coalesced. A sub-tile's trailing partial word is carried (shared memory) into the next sub-tile's first
+//      word. The tile's first word, when shared with the previous tile, is NOT stored: its bits go to
+//      head[tile] and a tiny second kernel ORs them into the word the previous tile wrote -- every output
+//      word has exactly one writer per kernel, no global atomics on the payload. The last tile adds the
+//      end-mark codeword and the 1-padding (reference include/canonical_huff_encoder.cc:255-257).
 #include "gh_common.cuh"
 
 namespace gh {
 
 constexpr int kEncThreads = 256;
 constexpr int kEncBytesPerThread = 16;
-constexpr int kEncTileBytes = kEncThreads * kEncBytesPerThread;
-// worst case per tile: 4096 symbols x 32 bits + end mark 32, plus one word of slack for the funnel shift
-constexpr int kEncStageWords = (kEncTileBytes * 32 + 32 + 31) / 32 + 2;
-constexpr int kEncBlocksPerSm = 6;
+constexpr int kEncSubTileBytes = kEncThreads * kEncBytesPerThread;  // 4 KiB
+constexpr int kEncSubTiles = 4;
+constexpr int kEncTileBytes = kEncSubTileBytes * kEncSubTiles;      // 16 KiB per look-back
+// worst case per sub-tile: 4096 symbols x 32 bits + end mark 32, plus slack for the funnel shift
+constexpr int kEncStageWords = (kEncSubTileBytes * 32 + 32 + 31) / 32 + 2;
+constexpr int kEncBlocksPerSm = 4;
 
 constexpr u64 kFlagMask = 3ull << 62;
 constexpr u64 kFlagAggregate = 1ull << 62;  // value = bits of this tile only
@@ -59,15 +64,21 @@ __device__ __forceinline__ void stage_bits(u32* stage, u32 pos, u64 acc, u32 len
   if (sh + len > 64) atomicOr(stage + w + 2, u32(v) << (32 - sh));
 }
 
+__device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
+  const u32 w = (k >> 2) == 0 ? v.x : (k >> 2) == 1 ? v.y : (k >> 2) == 2 ? v.z : v.w;
+  return (w >> (8 * (k & 3))) & 0xffu;
+}
+
 template <int kSymsPerChunk>
 __global__ void __launch_bounds__(kEncThreads)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
               u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
   constexpr int kChunks = kEncBytesPerThread / kSymsPerChunk;
   __shared__ u32 s_lut[GH_NSYM + 3];      // kSymsPerChunk == 4: (len << 16) | code ; else: code
-  __shared__ uint8_t s_len[GH_NSYM + 3];  // kSymsPerChunk == 2 only
-  __shared__ u32 s_stage[kEncStageWords];
-  __shared__ u32 s_warp_total[kEncThreads / 32];
+  __shared__ uint8_t s_len[GH_NSYM + 3];
+  __shared__ u32 s_stage[2][kEncStageWords];
+  __shared__ u32 s_warp_total[kEncSubTiles][kEncThreads / 32];
+  __shared__ u32 s_carry[2];
   __shared__ u32 s_tile;
   __shared__ u64 s_tile_start;
 
@@ -77,7 +88,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
     s_lut[s] = kSymsPerChunk == 4 ? ((u32(table.length[s]) << 16) | table.codeword[s]) : table.codeword[s];
     s_len[s] = table.length[s];
   }
-  for (unsigned i = t; i < unsigned(kEncStageWords); i += kEncThreads) s_stage[i] = 0;
+  for (unsigned i = t; i < 2u * kEncStageWords; i += kEncThreads) (&s_stage[0][0])[i] = 0;
   __syncthreads();
   const u64 ntiles = enc_num_tiles(n);
   const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
@@ -85,64 +96,65 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
 
   for (u64 tile = s_tile; tile < ntiles; tile = s_tile) {
     const bool last_tile = (tile + 1 == ntiles);
-    // ---- 1. load + gather + concatenate in registers ---------------------------------------------------
-    const u64 base = tile * kEncTileBytes + u64(t) * kEncBytesPerThread;
-    u32 w[4] = {0, 0, 0, 0};
-    int cnt = 0;
-    if (base + kEncBytesPerThread <= n) {
-      const uint4 v = ldg128(reinterpret_cast<const uint4*>(in + base));
-      w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
-      cnt = kEncBytesPerThread;
-    } else if (base < n) {
-      cnt = int(n - base);
-      const uint4 v = load_ragged(in + base, cnt);
-      w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
-    }
-    u64 chunk[kChunks];
-    u32 chunk_len[kChunks];
-    u32 my_bits = 0;
+    // ---- 1. all loads of the tile up front, bit count per sub-tile ---------------------------------------
+    uint4 raw[kEncSubTiles];
+    int cnt[kEncSubTiles];
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      u64 acc = 0;
-      u32 bits = 0;
-#pragma unroll
-      for (int j = 0; j < kSymsPerChunk; ++j) {
-        const int k = c * kSymsPerChunk + j;
-        const u32 b = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
-        u32 code, len;
-        if (kSymsPerChunk == 4) {
-          const u32 e = s_lut[b];
-          code = e & 0xffffu;
-          len = e >> 16;
-        } else {
-          code = s_lut[b];
-          len = s_len[b];
-        }
-        if (cnt != kEncBytesPerThread && k >= cnt) len = 0, code = 0;  // ragged last vector
-        acc = (acc << len) | code;  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
-        bits += len;
+    for (int j = 0; j < kEncSubTiles; ++j) {
+      const u64 base = tile * kEncTileBytes + u64(j) * kEncSubTileBytes + u64(t) * kEncBytesPerThread;
+      raw[j] = make_uint4(0, 0, 0, 0);
+      cnt[j] = 0;
+      if (base + kEncBytesPerThread <= n) {
+        raw[j] = ldg128(reinterpret_cast<const uint4*>(in + base));
+        cnt[j] = kEncBytesPerThread;
+      } else if (base < n) {
+        cnt[j] = int(n - base);
+        raw[j] = load_ragged(in + base, cnt[j]);
       }
-      chunk[c] = acc;
-      chunk_len[c] = bits;
-      my_bits += bits;
     }
-    // the owner of the last byte also carries the end mark
-    const bool owns_end = append_eof && last_tile && (base < n) && (base + kEncBytesPerThread >= n);
-    const u32 eof_len = owns_end ? eof_len_all : 0u;
-    my_bits += eof_len;
-
-    // ---- 2. block scan; warp 0 resolves the global offset while the others pack ------------------------
-    const u32 incl = warp_inclusive_scan(my_bits, lane);
-    if (lane == 31) s_warp_total[warp] = incl;
-    __syncthreads();  // (a)
-    u32 warp_base = 0, tile_bits = 0;
+    u32 bits[kEncSubTiles];
+    int end_sub = -1;  // the sub-tile in which this thread owns the last input byte (it carries the end mark)
 #pragma unroll
-    for (int k = 0; k < kEncThreads / 32; ++k) {
-      const u32 wt = s_warp_total[k];
-      if (unsigned(k) < warp) warp_base += wt;
-      tile_bits += wt;
+    for (int j = 0; j < kEncSubTiles; ++j) {
+      u32 b = 0;
+      if (cnt[j] == kEncBytesPerThread) {
+#pragma unroll
+        for (int k = 0; k < kEncBytesPerThread; ++k) b += s_len[vec_byte(raw[j], k)];
+      } else {
+        for (int k = 0; k < cnt[j]; ++k) b += s_len[vec_byte(raw[j], k)];
+      }
+      const u64 base = tile * kEncTileBytes + u64(j) * kEncSubTileBytes + u64(t) * kEncBytesPerThread;
+      if (append_eof && last_tile && base < n && base + kEncBytesPerThread >= n) {
+        end_sub = j;
+        b += eof_len_all;
+      }
+      bits[j] = b;
     }
-    u32 pos = warp_base + incl - my_bits;  // tile-relative bit position of this thread's first bit
+
+    // ---- 2. per-sub-tile block scans; warp 0 resolves the global offset while the others start packing ----
+    u32 incl[kEncSubTiles];
+#pragma unroll
+    for (int j = 0; j < kEncSubTiles; ++j) {
+      incl[j] = warp_inclusive_scan(bits[j], lane);
+      if (lane == 31) s_warp_total[j][warp] = incl[j];
+    }
+    __syncthreads();  // (a)
+    u32 sub_bits[kEncSubTiles];  // bits of each sub-tile
+    u32 pos0[kEncSubTiles];      // sub-tile-relative bit position of this thread's first bit
+    u32 tile_bits = 0;
+#pragma unroll
+    for (int j = 0; j < kEncSubTiles; ++j) {
+      u32 wb = 0, tot = 0;
+#pragma unroll
+      for (int k = 0; k < kEncThreads / 32; ++k) {
+        const u32 wt = s_warp_total[j][k];
+        if (unsigned(k) < warp) wb += wt;
+        tot += wt;
+      }
+      sub_bits[j] = tot;
+      pos0[j] = wb + incl[j] - bits[j];
+      tile_bits += tot;
+    }
 
     if (warp == 0) {
       u64 exclusive = start_bit;
@@ -173,35 +185,69 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       if (lane == 0) s_tile_start = exclusive;
     }
 
-    // ---- 3. pack at tile-relative positions -----------------------------------------------------------
+    // ---- 3 + 4. sub-tile by sub-tile: pack (tile-relative), then copy out with the phase shift ------------
+    u32 before = 0;  // bits of this tile in earlier sub-tiles
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      if (chunk_len[c]) stage_bits(s_stage, pos, chunk[c], chunk_len[c]);
-      pos += chunk_len[c];
-    }
-    if (eof_len) stage_bits(s_stage, pos, eof_code, eof_len);
-    __syncthreads();  // (c) staging complete, s_tile_start written
-    if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);  // next tile for this block (read after barrier (d))
+    for (int j = 0; j < kEncSubTiles; ++j) {
+      u32* stage = s_stage[j & 1];
+      {
+        u32 pos = pos0[j];
+        const bool full = cnt[j] == kEncBytesPerThread;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          u64 acc = 0;
+          u32 clen = 0;
+#pragma unroll
+          for (int q = 0; q < kSymsPerChunk; ++q) {
+            const int k = c * kSymsPerChunk + q;
+            const u32 b = vec_byte(raw[j], k);
+            u32 code, len;
+            if (kSymsPerChunk == 4) {
+              const u32 e = s_lut[b];
+              code = e & 0xffffu;
+              len = e >> 16;
+            } else {
+              code = s_lut[b];
+              len = s_len[b];
+            }
+            if (!full && k >= cnt[j]) len = 0, code = 0;  // ragged last vector of the input
+            acc = (acc << len) | code;  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
+            clen += len;
+          }
+          if (clen) stage_bits(stage, pos, acc, clen);
+          pos += clen;
+        }
+        if (end_sub == j && eof_len_all) stage_bits(stage, pos, eof_code, eof_len_all);
+      }
+      __syncthreads();  // (c_j) staging of sub-tile j complete; for j == 0 also: s_tile_start written
+      if (j == 0 && t == 0) s_tile = atomicAdd(ws.ticket, 1u);  // next tile (read after the last barrier below)
 
-    // ---- 4. copy-out with the phase shift; one writer per output word -----------------------------------
-    const u64 G = s_tile_start;
-    const u32 phase = u32(G & 31);
-    const u64 end_bit = G + tile_bits;  // first bit after this tile (after the end mark on the last tile)
-    u32 pad = 0;
-    if (append_eof && last_tile) pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s up to the byte boundary
-    if (last_tile && t == 0 && end_bit_out) *end_bit_out = end_bit;
-    const u64 word0 = G >> 5;
-    const u32 nwords = u32((u64(phase) + tile_bits + pad + 31) >> 5);
-    const bool shared_head = (tile > 0) && (phase != 0);
-    for (u32 i = t; i < nwords; i += kEncThreads) {
-      u32 v = __funnelshift_r(s_stage[i], i ? s_stage[i - 1] : 0u, phase);
-      const u64 gw = word0 + i;
-      if (pad && gw == (end_bit >> 5)) v |= ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad));
-      if (i == 0 && shared_head) ws.head[tile] = v;
-      else if (gw < out_word_cap) out_words[gw] = be32(v);
+      const u64 G = s_tile_start + before;  // global bit offset of this sub-tile
+      const u32 nbits = sub_bits[j];
+      const u32 phase = u32(G & 31);
+      const u64 end_bit = G + nbits;
+      const bool stream_end = last_tile && (before + nbits == tile_bits);  // no bits follow in the whole stream
+      const bool more_in_tile = before + nbits < tile_bits;                // a later sub-tile continues this word
+      u32 pad = 0;
+      if (append_eof && stream_end && nbits) pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s to the byte
+      if (stream_end && nbits && t == 0 && end_bit_out) *end_bit_out = end_bit;
+      const u64 word0 = G >> 5;
+      const u32 nwords = nbits ? u32((u64(phase) + nbits + pad + 31) >> 5) : 0u;
+      const bool partial_end = ((phase + nbits + pad) & 31) != 0;
+      const bool shared_head = (j == 0) && (tile > 0) && (phase != 0);
+      for (u32 i = t; i < nwords; i += kEncThreads) {
+        u32 v = __funnelshift_r(stage[i], i ? stage[i - 1] : 0u, phase);
+        const u64 gw = word0 + i;
+        if (pad && gw == (end_bit >> 5)) v |= ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad));
+        if (i == 0 && j > 0 && phase != 0) v |= s_carry[(j - 1) & 1];  // tail of the previous sub-tile
+        if (i == nwords - 1 && partial_end && more_in_tile) s_carry[j & 1] = v;  // continued by the next sub-tile
+        else if (i == 0 && shared_head) ws.head[tile] = v;
+        else if (gw < out_word_cap) out_words[gw] = be32(v);
+      }
+      __syncthreads();  // (d_j) staged words consumed
+      for (u32 i = t; i < (nbits >> 5) + 3; i += kEncThreads) stage[i] = 0;  // clean for sub-tile j + 2
+      before += nbits;
     }
-    __syncthreads();  // (d) staged words consumed, s_tile updated
-    for (u32 i = t; i < (tile_bits >> 5) + 2; i += kEncThreads) s_stage[i] = 0;  // clean for the next tile
   }
 }
 

@@ -372,17 +372,15 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
 }
 
 // ---- K5b: one synchronisation round ------------------------------------------------------------------------
-struct SmemSync {
-  SmemCanon canon;
-  uint16_t lut1[1 << kLut1Bits];
-};
 
 __global__ void __launch_bounds__(kDecThreads)
 dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
-  __shared__ SmemSync s;
+  __shared__ SmemSpeculate s;
   load_canon(s.canon, ws.tables);
   for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
     reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
+  for (unsigned i = threadIdx.x; i < (1u << kLutCBits) / 16; i += kDecThreads)
+    reinterpret_cast<uint4*>(s.lutC)[i] = reinterpret_cast<const uint4*>(ws.lutC)[i];
   __syncthreads();
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
   u64 mine = 0;
@@ -405,6 +403,12 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
     BitReader ra, rb;
     ra.seek(g.payload, g.readable, start + pos_a);
     rb.seek(g.payload, g.readable, start + pos_b);
+    // Both paths take the same kind of step from a given position (as many whole codewords as fit in 15 bits
+    // while that window lies inside the subsequence, else one codeword), so equal positions mean equal futures.
+    // A boundary that one path steps over can be a stepping point of the other: they then meet a little later,
+    // or not at all inside the subsequence -- in which case B has simply been walked to its end, which is exact.
+    const bool bulk = end >= u32(kLutCBits);
+    const u32 last = end - u32(kLutCBits);
     while (pos_b < end) {
       if (pos_a == pos_b) {
         merged = true;
@@ -412,18 +416,32 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
       }
       u32 sym, len;
       if (pos_a < pos_b) {
-        decode_one(s.canon, s.lut1, ra.window(), sym, len);
-        ++steps_a;
-        eofs_a += sym == u32(GH_EOF_SYMBOL);
+        const u32 win = ra.window();
+        const u32 e = (bulk && pos_a <= last) ? u32(s.lutC[win >> (32 - kLutCBits)]) : 0u;
+        if (e) {
+          len = e & 15u;
+          steps_a += e >> 4;
+        } else {
+          decode_one(s.canon, s.lut1, win, sym, len);
+          ++steps_a;
+          eofs_a += sym == u32(GH_EOF_SYMBOL);
+        }
         pos_a += len;
         ra.consume(len);
       } else {
-        decode_one(s.canon, s.lut1, rb.window(), sym, len);
-        if (sym == u32(GH_EOF_SYMBOL)) {
-          if (!eofs_b) first_b = steps_b;
-          ++eofs_b;
+        const u32 win = rb.window();
+        const u32 e = (bulk && pos_b <= last) ? u32(s.lutC[win >> (32 - kLutCBits)]) : 0u;
+        if (e) {
+          len = e & 15u;
+          steps_b += e >> 4;
+        } else {
+          decode_one(s.canon, s.lut1, win, sym, len);
+          if (sym == u32(GH_EOF_SYMBOL)) {
+            if (!eofs_b) first_b = steps_b;
+            ++eofs_b;
+          }
+          ++steps_b;
         }
-        ++steps_b;
         pos_b += len;
         rb.consume(len);
       }
@@ -578,8 +596,8 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
 }
 
 // ---- K7: final decode from the exact entries ------------------------------------------------------------------
-// Up to 3 codewords per lookup (13-bit window); symbols are collected 8 at a time in a 64-bit register and four
-// such registers leave as one full 32-byte sector (the first few symbols go out as bytes to reach alignment).
+// Up to 3 codewords per lookup (13-bit window); symbols are collected 8 at a time in a 64-bit register and two
+// such registers leave as one 128-bit store (the first few symbols go out as bytes to reach alignment).
 struct SmemWrite {
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
@@ -613,18 +631,18 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
     if (unsigned(k) < warp) warp_base += s.warp_total[k];
   const u64 o = ws.tile_base[blockIdx.x] + warp_base + (incl - count);
   if (count == 0 || o >= out_cap) return;
-  u64 remaining = count;
-  if (remaining > out_cap - o) remaining = out_cap - o;
+  u32 remaining = count;
+  if (u64(remaining) > out_cap - o) remaining = u32(out_cap - o);
 
   const u64 start = i * u64(g.sub_bytes) * 8;
   u32 pos = st_entry(st);  // bits of the subsequence consumed so far
   uint8_t* dst = out + o;
   u32 sym, len;
-  // head: single symbols up to the first 32-byte boundary of the output
+  // head: single symbols up to the first 16-byte boundary of the output
   {
     BitReader r;
     r.seek(g.payload, g.readable, start + pos);
-    while (remaining && (reinterpret_cast<uintptr_t>(dst) & 31)) {
+    while (remaining && (reinterpret_cast<uintptr_t>(dst) & 15)) {
       decode_one(s.canon, s.lut1, r.window(), sym, len);
       r.consume(len);
       pos += len;
@@ -632,93 +650,91 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
       --remaining;
     }
   }
-  // body: `acc` collects symbols (first symbol in the lowest byte); every 8 symbols it is retired into
-  // held[0..2], and the fourth retirement writes one whole 32-byte sector as two back-to-back 128-bit stores
-  // (lanes write to scattered places, so anything narrower leaves L2 with partially written sectors).
-  // The bit stream side is word-synchronous as in K5a: one unconditional 32-bit push per step from a statically
-  // indexed register, then table lookups while >= 32 bits are held.
-  u64 acc = 0, held0 = 0, held1 = 0, held2 = 0;
-  u32 nacc = 0;   // symbols in acc (0..7 between steps)
-  u32 nheld = 0;  // retired 8-symbol groups waiting in held0..2
+  // body: one table lookup per iteration for every lane. Everything that happens only now and then per lane
+  // (32-bit refill, 128-bit reload, retiring 8 collected symbols, every second retirement a 128-bit store) is
+  // short straight-line code: with 32 lanes out of step, "now and then per lane" is "every iteration per warp",
+  // so the loop is written to make those paths cheap rather than rare.
+  u64 acc = 0, held = 0;
+  u32 nacc = 0;  // symbols in acc (0..7 between iterations), first symbol in the lowest byte
+  bool have_held = false;
   auto emit = [&](u32 syms, u32 n) {
     const u32 sh = nacc * 8;
     acc |= u64(syms) << sh;
     nacc += n;
     if (nacc >= 8) {
       const u64 spill = sh > 40 ? u64(syms) >> (64 - sh) : 0ull;  // bytes that did not fit
-      if (nheld == 3) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-        d4[0] = make_uint4(u32(held0), u32(held0 >> 32), u32(held1), u32(held1 >> 32));
-        d4[1] = make_uint4(u32(held2), u32(held2 >> 32), u32(acc), u32(acc >> 32));
-        dst += 32;
-        nheld = 0;
+      if (have_held) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(u32(held), u32(held >> 32), u32(acc), u32(acc >> 32));
+        dst += 16;
       } else {
-        if (nheld == 0) held0 = acc;
-        else if (nheld == 1) held1 = acc;
-        else held2 = acc;
-        ++nheld;
+        held = acc;
       }
+      have_held = !have_held;
       acc = spill;
       nacc -= 8;
     }
   };
   {
     const u64 bit0 = start + pos;
-    u64 v = bit0 >> 7;
-    u32 k0 = u32(bit0 >> 5) & 3u;
-    u32 drop = u32(bit0) & 31u;
+    const u64 v0 = bit0 >> 7;
     const u64 full_vecs = g.readable >> 4;
-    if (remaining >= u64(kLutWMaxSyms) && v + 1 < full_vecs) {
-      const uint4* vp = reinterpret_cast<const uint4*>(g.payload);
-      uint4 cur = ldg128(vp + v), nxt = ldg128(vp + v + 1);
+    if (remaining >= u32(kLutWMaxSyms) && v0 + 2 < full_vecs) {
+      const uint4* vp = reinterpret_cast<const uint4*>(g.payload) + v0;  // vector indices below are relative to v0
+      uint4 cur = ldg128(vp), ahead = ldg128(vp + 1);
+      u32 vnext = 2;  // next vector to request
+      const u64 span = full_vecs - v0;
+      const u32 vend = span > 0x7fffffffull ? 0x7fffffffu : u32(span);  // vectors that may be requested
+      u32 w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
+      const u32 skip = u32(bit0 >> 5) & 3u;
+      for (u32 k = 0; k < skip; ++k) w0 = w1, w1 = w2, w2 = w3;
+      u32 left = 4 - skip;
       u64 buf = 0;
       int avail = 0;
-      bool more = true;
-      while (more) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (u32(k) < k0) continue;
-          const u32 w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
-          buf |= u64(be32(w)) << (32 - avail);
-          avail += 32;
-          if (drop) buf <<= drop, avail -= int(drop), drop = 0;
-          while (avail >= 32 && remaining >= u64(kLutWMaxSyms)) {  // an entry yields at most kLutWMaxSyms symbols
-            const u32 win = u32(buf >> 32);
-            const u32 e = s.lutW[win >> (32 - kLutWBits)];
-            u32 n, syms;
-            if (e) {
-              len = e & 15u;
-              n = (e >> 4) & 3u;
-              syms = e >> 8;
-            } else {  // codeword longer than 13 bits (the end mark cannot occur: the count stops before it)
-              decode_one(s.canon, s.lut1, win, sym, len);
-              n = 1;
-              syms = sym & 0xffu;
-            }
-            pos += len;
-            buf <<= len;
-            avail -= int(len);
-            remaining -= n;
-            emit(syms, n);
-          }
-          if (remaining < u64(kLutWMaxSyms)) {
-            more = false;
-            break;
-          }
+      auto push = [&]() {
+        buf |= u64(be32(w0)) << (32 - avail);
+        avail += 32;
+        w0 = w1, w1 = w2, w2 = w3;
+        if (--left == 0) {
+          w0 = ahead.x, w1 = ahead.y, w2 = ahead.z, w3 = ahead.w;
+          left = 4;
+          ahead = ldg128(vp + vnext);  // vnext < vend is the loop condition
+          ++vnext;
         }
-        k0 = 0;
-        if (!more) break;
-        ++v;
-        if (v + 1 >= full_vecs) break;
-        cur = nxt;
-        nxt = ldg128(vp + v + 1);
+      };
+      push();
+      push();
+      {
+        const u32 drop = u32(bit0) & 31u;
+        buf <<= drop;
+        avail -= int(drop);
+        if (avail < 32) push();
+      }
+      while (remaining >= u32(kLutWMaxSyms) && vnext < vend) {
+        const u32 win = u32(buf >> 32);
+        const u32 e = s.lutW[win >> (32 - kLutWBits)];
+        u32 n, syms;
+        if (e) {
+          len = e & 15u;
+          n = (e >> 4) & 3u;
+          syms = e >> 8;
+        } else {  // codeword longer than 13 bits (the end mark cannot occur: the count stops before it)
+          decode_one(s.canon, s.lut1, win, sym, len);
+          n = 1;
+          syms = sym & 0xffu;
+        }
+        pos += len;
+        buf <<= len;
+        avail -= int(len);
+        remaining -= n;
+        if (avail < 32) push();
+        emit(syms, n);
       }
     }
   }
   // what the bulk loop left (payload tail or the last couple of symbols): bounds-checked reader from `pos`
   BitReader r;
   r.seek(g.payload, g.readable, start + pos);
-  while (remaining >= u64(kLutWMaxSyms)) {
+  while (remaining >= u32(kLutWMaxSyms)) {
     const u32 win = r.window();
     const u32 e = s.lutW[win >> (32 - kLutWBits)];
     u32 n, syms;
@@ -736,9 +752,7 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
     emit(syms, n);
   }
   // drain what is collected, then the last few symbols one by one
-  if (nheld > 0) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held0), u32(held0 >> 32)), dst += 8;
-  if (nheld > 1) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held1), u32(held1 >> 32)), dst += 8;
-  if (nheld > 2) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held2), u32(held2 >> 32)), dst += 8;
+  if (have_held) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held), u32(held >> 32)), dst += 8;
   for (u32 k = 0; k < nacc; ++k) *dst++ = uint8_t(acc >> (8 * k));
   while (remaining) {
     decode_one(s.canon, s.lut1, r.window(), sym, len);
@@ -835,8 +849,9 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
               const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW));
     g.sub_bytes = choose_sub_bytes(slice_bytes);
     // near-fixed-length codes (all lengths within one bit: uniform-looking bytes) re-synchronise only when one of
-    // the rare longer codewords shifts the phase; start them 2x coarser (rounds cost one subsequence walk each)
-    if (code->max_len - code->min_len <= 1 && u64(g.sub_bytes) * 2 <= kMaxSubBytes) g.sub_bytes *= 2;
+    // the rare longer codewords shifts the phase; start them 4x coarser (measured on uniform bytes: the paths need
+    // ~5.7k symbols on average to meet)
+    if (code->max_len - code->min_len <= 1 && u64(g.sub_bytes) * 4 <= kMaxSubBytes) g.sub_bytes *= 4;
   } else {
     GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
     GH_CUDA_TRY(cudaStreamSynchronize(stream));

@@ -27,6 +27,8 @@
 //
 // Algorithmic traffic: C bytes read + N bytes written; this implementation reads the payload twice
 // (speculate + write), which the roofline accounting in bench.py does NOT credit.
+#include <stdlib.h>
+
 #include "gh_common.cuh"
 
 namespace gh {
@@ -70,10 +72,12 @@ struct DecWorkspace {
   const uint16_t* lut1;        // [2^12]  device-built, see gh_internal.h
   const uint8_t* lutC;         // [2^15]
   const u32* lutW;             // [2^13]
+  const u32* lutP;             // [2^12]
   DecControl* ctl;
   u64* sub;        // [n_sub]
   u32* neof;       // [n_sub]  end-mark codewords on each subsequence's path
   u32* eofpos;     // [n_sub]  symbols before the path's first end mark, kEofPosUnknown if it was not observed
+  u64* out_off;    // [n_sub]  output offset of each subsequence's first symbol
   u64* tile_sum;   // [n_tiles]
   u64* tile_base;  // [n_tiles]
 };
@@ -130,7 +134,7 @@ __device__ __forceinline__ void decode_one(const SmemCanon& s, const uint16_t* l
 // thread w handles window value w of each table it is in range for
 __global__ void __launch_bounds__(256)
 dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restrict__ lut1, uint8_t* __restrict__ lutC,
-                      u32* __restrict__ lutW) {
+                      u32* __restrict__ lutW, u32* __restrict__ lutP) {
   __shared__ SmemCanon s;
   load_canon(s, tables);
   __syncthreads();
@@ -161,6 +165,12 @@ dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restr
   if (w < (1u << kLutWBits)) {
     walk(w, kLutWBits, kLutWMaxSyms, tl, ns, pk);
     lutW[w] = ns ? (tl | (ns << 4) | (pk << 8)) : 0u;
+  }
+  if (w < (1u << kLutPBits)) {
+    walk(w, kLutPBits, 2, tl, ns, pk);
+    u32 s1, l1 = 0;
+    if (ns) canon_search(s, w << (32 - kLutPBits), min_len, s1, l1);
+    lutP[w] = ns ? (tl | (ns << 4) | (l1 << 6) | ((pk & 0xffffu) << 16)) : 0u;
   }
   if (w < (1u << kLut1Bits)) {
     // single codeword, end mark included (as symbol 256); 0 when it does not fit in 12 bits
@@ -762,9 +772,206 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   }
 }
 
+// ---- K6b: per-subsequence output offsets (for the warp-cooperative writer) -----------------------------------
+__global__ void __launch_bounds__(kDecThreads)
+dec_sub_offsets_kernel(DecGeometry g, DecWorkspace ws) {
+  __shared__ u32 s_warp[kDecThreads / 32];
+  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const u64 i = u64(blockIdx.x) * kDecThreads + t;
+  const u32 eof_index = ws.ctl->eof_index;
+  u32 count = 0;
+  if (i < g.n_sub && i <= u64(eof_index)) count = i == u64(eof_index) ? ws.ctl->eof_prefix : st_count(ws.sub[i]);
+  const u32 incl = warp_inclusive_scan(count, lane);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  u32 warp_base = 0;
+#pragma unroll
+  for (int k = 0; k < kDecThreads / 32; ++k)
+    if (unsigned(k) < warp) warp_base += s_warp[k];
+  if (i < g.n_sub) ws.out_off[i] = ws.tile_base[blockIdx.x] + warp_base + (incl - count);
+}
+
+// ---- K7 (warp-cooperative): one warp per subsequence, shared-memory staging on both sides ---------------------
+// A subsequence's exact entry and symbol count are known, but a single thread walking it pays for every per-lane
+// event (refill, reload, retiring output registers) on every iteration, because 32 lanes are never in step.
+// Here a warp takes the subsequence in 2 KiB segments instead:
+//   stage   coalesced 128-bit loads of the segment into shared memory (stream order, one pad word per 16 so that
+//           the 32 lanes' pieces start in 32 different banks);
+//   pass A  lane l walks the 64-byte piece l of the segment from its start, counting codewords (lane 0 starts at
+//           the exact entry): bit-addressed windows straight from shared memory, no refill state at all;
+//   fix-up  lanes pass their exits to the right (shuffle); a lane whose assumed entry was wrong walks old and new
+//           path in lockstep until they meet (a few codewords) and patches its count; repeated until no exit moves
+//           -- the same fixed-point argument as K5b, inside a warp and without touching memory;
+//   scan    warp scan of the counts -> each lane's position in the segment's output;
+//   pass B  lanes decode again from their exact entries and store symbols as bytes into a shared output window;
+//   copy    the window leaves as coalesced 128-bit stores (its phase in shared memory equals the destination's).
+// Every lane does the same thing in every iteration; the only divergence left is the trip count of the piece loop.
+constexpr int kWriteWarps = 16;
+constexpr u32 kPieceBits = 512;
+constexpr u32 kSegBits = 32 * kPieceBits;             // 2 KiB of payload per segment
+constexpr u32 kSegStageVecs = kSegBits / 128 + 3;     // + alignment slack (entry < 128 bits) + look-ahead
+constexpr u32 kSegStageWords = kSegStageVecs * 4;
+constexpr u32 kSegPaddedWords = kSegStageWords + kSegStageWords / 16 + 1;
+constexpr u32 kOutWindow = 3072;                      // symbols per copy-out window (multiple of 16)
+
+struct SmemWriteWarp {
+  SmemCanon canon;
+  u32 lutP[1 << kLutPBits];
+  u32 in[kWriteWarps][kSegPaddedWords];
+  __align__(16) uint8_t out[kWriteWarps][kOutWindow + 32];
+};
+
+__device__ __forceinline__ u32 seg_window(const u32* sin, u32 pos) {
+  const u32 j = pos >> 5;
+  const u32 a = j + (j >> 4), b = (j + 1) + ((j + 1) >> 4);
+  return __funnelshift_l(sin[b], sin[a], pos & 31);
+}
+
+// one step of a path inside a piece: one or two whole codewords, never a second one once the first reaches p_end
+__device__ __forceinline__ void piece_step(const SmemWriteWarp& s, const u32* sin, u32 p_end, u32& pos, u32& cnt) {
+  const u32 win = seg_window(sin, pos);
+  const u32 e = s.lutP[win >> (32 - kLutPBits)];
+  if (e) {
+    const u32 len1 = (e >> 6) & 15u;
+    const bool both = ((e >> 4) & 3u) == 2u && pos + len1 < p_end;
+    pos += both ? (e & 15u) : len1;
+    cnt += both ? 2u : 1u;
+  } else {  // longer than 12 bits, or the end mark (runs through like any codeword; counts are trimmed later)
+    u32 sym, len;
+    canon_search(s.canon, win, s.canon.min_len, sym, len);
+    pos += len;
+    ++cnt;
+  }
+}
+
+__global__ void __launch_bounds__(kWriteWarps * 32)
+dec_write_warp_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
+  GH_DYNAMIC_SMEM(smem_raw);
+  SmemWriteWarp& s = *reinterpret_cast<SmemWriteWarp*>(smem_raw);
+  load_canon(s.canon, ws.tables);
+  for (unsigned k = threadIdx.x; k < (1u << kLutPBits) / 4; k += kWriteWarps * 32)
+    reinterpret_cast<uint4*>(s.lutP)[k] = reinterpret_cast<const uint4*>(ws.lutP)[k];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u64 i = u64(blockIdx.x) * kWriteWarps + wib;
+  u32* sin = s.in[wib];
+  uint8_t* sout = s.out[wib];
+
+  // everything below is warp-uniform control flow around warp-synchronous phases
+  u32 remaining = 0;
+  u64 o = 0, bitpos = 0;
+  if (i < g.n_sub) {
+    const u32 eof_index = ws.ctl->eof_index;
+    const u64 st = ws.sub[i];
+    if (i <= u64(eof_index)) remaining = i == u64(eof_index) ? ws.ctl->eof_prefix : st_count(st);
+    o = ws.out_off[i];
+    if (o >= out_cap) remaining = 0;
+    else if (u64(remaining) > out_cap - o) remaining = u32(out_cap - o);
+    bitpos = i * u64(g.sub_bytes) * 8 + st_entry(st);
+  }
+  const u64 full_vecs = g.readable >> 4;
+  while (remaining > 0) {
+    // ---- stage the segment that starts at the 16-byte vector holding `bitpos` ------------------------------
+    const u64 vec0 = bitpos >> 7;
+    const u32 first = u32(bitpos & 127);  // the exact entry, as a bit offset into the staged words
+    for (u32 k = lane; k < kSegStageVecs; k += 32) {
+      const u64 v = vec0 + k;
+      const uint4 q = v < full_vecs ? ldg128(reinterpret_cast<const uint4*>(g.payload) + v)
+                                    : fetch_tail(g.payload, g.readable, v);
+      const u32 j = 4 * k, base = j + (j >> 4);
+      sin[base] = be32(q.x);
+      sin[base + 1] = be32(q.y);
+      sin[base + 2] = be32(q.z);
+      sin[base + 3] = be32(q.w);
+    }
+    __syncwarp();
+    // ---- pass A: count the codewords of my piece, starting at its first bit (lane 0: at the exact entry) ----
+    const u32 p_begin = first + lane * kPieceBits, p_end = p_begin + kPieceBits;
+    u32 entry = p_begin, cnt = 0, pos = p_begin;
+    while (pos < p_end) piece_step(s, sin, p_end, pos, cnt);
+    u32 exit = pos - p_end;
+    // ---- fix-up: entries from the left neighbours' exits, until no exit moves ------------------------------
+    while (true) {
+      const u32 left_exit = __shfl_up_sync(0xffffffffu, exit, 1);
+      const u32 want = lane == 0 ? entry : p_begin + left_exit;
+      bool moved = false;
+      if (want != entry) {
+        u32 pa = entry, pb = want, sa = 0, sb = 0;
+        bool merged = false;
+        while (pb < p_end) {
+          if (pa == pb) {
+            merged = true;
+            break;
+          }
+          if (pa < pb) piece_step(s, sin, p_end, pa, sa);
+          else piece_step(s, sin, p_end, pb, sb);
+        }
+        if (merged) {
+          cnt = sb + (cnt - sa);
+        } else {
+          cnt = sb;
+          moved = (pb - p_end) != exit;
+          exit = pb - p_end;
+        }
+        entry = want;
+      }
+      if (!__any_sync(0xffffffffu, moved)) break;
+    }
+    // ---- scan, trim to what this subsequence still owes ---------------------------------------------------------
+    const u32 incl = warp_inclusive_scan(cnt, lane);
+    const u32 prefix = incl - cnt;
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    const u32 seg_syms = total < remaining ? total : remaining;
+    const u32 my_end = prefix >= seg_syms ? prefix : (incl < seg_syms ? incl : seg_syms);  // my symbols: [prefix, my_end)
+    const u32 last_exit = __shfl_sync(0xffffffffu, exit, 31);
+    // ---- pass B + copy-out, one output window at a time -------------------------------------------------------
+    const u32 a0 = u32(reinterpret_cast<uintptr_t>(out + o) & 15);  // window phase == destination phase
+    u32 idx = prefix;  // segment-relative index of my next symbol
+    pos = entry;
+    for (u32 wbase = 0; wbase < seg_syms; wbase += kOutWindow) {
+      const u32 wend = wbase + kOutWindow < seg_syms ? wbase + kOutWindow : seg_syms;
+      const u32 lim = my_end < wend ? my_end : wend;
+      uint8_t* slot = sout + a0 - wbase;  // slot[idx] is where symbol idx of the segment goes
+      while (idx < lim) {
+        const u32 win = seg_window(sin, pos);
+        const u32 e = s.lutP[win >> (32 - kLutPBits)];
+        if (e) {
+          const bool both = ((e >> 4) & 3u) == 2u && idx + 1 < lim;
+          slot[idx] = uint8_t(e >> 16);
+          if (both) slot[idx + 1] = uint8_t(e >> 24);
+          pos += both ? (e & 15u) : ((e >> 6) & 15u);
+          idx += both ? 2u : 1u;
+        } else {
+          u32 sym, len;
+          canon_search(s.canon, win, s.canon.min_len, sym, len);
+          slot[idx] = uint8_t(sym);
+          pos += len;
+          ++idx;
+        }
+      }
+      __syncwarp();
+      const u32 m = wend - wbase;  // bytes in this window, at sout[a0 .. a0 + m)
+      uint8_t* dst = out + o + wbase;
+      const u32 head = a0 ? ((16 - a0) < m ? (16 - a0) : m) : 0u;
+      if (lane < head) dst[lane] = sout[a0 + lane];
+      const u32 nvec = (m - head) >> 4;
+      const uint4* src4 = reinterpret_cast<const uint4*>(sout + a0 + head);
+      uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
+      for (u32 k = lane; k < nvec; k += 32) dst4[k] = src4[k];
+      const u32 done = head + (nvec << 4);
+      if (lane < m - done) dst[done + lane] = sout[a0 + done + lane];
+      __syncwarp();
+    }
+    // ---- next segment starts at the boundary after the last piece ---------------------------------------------
+    bitpos = (vec0 << 7) + first + kSegBits + last_exit;
+    remaining -= seg_syms;
+    o += seg_syms;
+  }
+}
+
 // ---- host orchestration -------------------------------------------------------------------------------
 struct DecLayout {
-  size_t off_tables, off_lut1, off_lutC, off_lutW, off_ctl, off_sub, off_neof, off_eofpos, off_tile_sum, off_tile_base, total;
+  size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_tile_sum, off_tile_base, total;
 };
 
 static DecLayout dec_layout(u64 slice_bytes) {
@@ -776,11 +983,13 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_lut1 = up(sizeof(DecodeTables));
   L.off_lutC = L.off_lut1 + up(sizeof(uint16_t) << kLut1Bits);
   L.off_lutW = L.off_lutC + up(sizeof(uint8_t) << kLutCBits);
-  L.off_ctl = L.off_lutW + up(sizeof(u32) << kLutWBits);
+  L.off_lutP = L.off_lutW + up(sizeof(u32) << kLutWBits);
+  L.off_ctl = L.off_lutP + up(sizeof(u32) << kLutPBits);
   L.off_sub = L.off_ctl + 256;
   L.off_neof = L.off_sub + up(size_t(max_sub) * 8);
   L.off_eofpos = L.off_neof + up(size_t(max_sub) * 4);
-  L.off_tile_sum = L.off_eofpos + up(size_t(max_sub) * 4);
+  L.off_out_off = L.off_eofpos + up(size_t(max_sub) * 4);
+  L.off_tile_sum = L.off_out_off + up(size_t(max_sub) * 8);
   L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
   L.total = L.off_tile_base + up(size_t(max_tiles) * 8);
   return L;
@@ -793,10 +1002,12 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   w.lut1 = reinterpret_cast<const uint16_t*>(p + L.off_lut1);
   w.lutC = reinterpret_cast<const uint8_t*>(p + L.off_lutC);
   w.lutW = reinterpret_cast<const u32*>(p + L.off_lutW);
+  w.lutP = reinterpret_cast<const u32*>(p + L.off_lutP);
   w.ctl = reinterpret_cast<DecControl*>(p + L.off_ctl);
   w.sub = reinterpret_cast<u64*>(p + L.off_sub);
   w.neof = reinterpret_cast<u32*>(p + L.off_neof);
   w.eofpos = reinterpret_cast<u32*>(p + L.off_eofpos);
+  w.out_off = reinterpret_cast<u64*>(p + L.off_out_off);
   w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
   w.tile_base = reinterpret_cast<u64*>(p + L.off_tile_base);
   return w;
@@ -816,6 +1027,7 @@ static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* 
   GH_LAUNCH(dec_tile_sum_kernel, tiles, kDecThreads, 0, stream, g, ws);
   GH_LAUNCH(dec_locate_eof_kernel, 1, kDecThreads, 0, stream, g, ws);
   GH_LAUNCH(dec_offsets_kernel, 1, kScanThreads, 0, stream, g, ws);
+  GH_LAUNCH(dec_sub_offsets_kernel, tiles, kDecThreads, 0, stream, g, ws);
   int rc = check_launch();
   if (rc != GH_OK) return rc;
   GH_CUDA_TRY(cudaMemcpyAsync(h_ctl, ws.ctl, sizeof(DecControl), cudaMemcpyDeviceToHost, stream));
@@ -846,7 +1058,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     if (rc != GH_OK) return rc;
     GH_CUDA_TRY(cudaMemcpyAsync(const_cast<DecodeTables*>(ws.tables), &tables, sizeof(tables), cudaMemcpyHostToDevice, stream));
     GH_LAUNCH(dec_build_luts_kernel, (1u << kLutCBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
-              const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW));
+              const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW), const_cast<u32*>(ws.lutP));
     g.sub_bytes = choose_sub_bytes(slice_bytes);
     // near-fixed-length codes (all lengths within one bit: uniform-looking bytes) re-synchronise only when one of
     // the rare longer codewords shifts the phase; start them 4x coarser (measured on uniform bytes: the paths need
@@ -918,11 +1130,31 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   return GH_OK;
 }
 
+static bool use_thread_writer() {  // GH_WRITE_KERNEL=thread selects the one-thread-per-subsequence writer (A/B runs)
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("GH_WRITE_KERNEL");
+    cached = (e && e[0] == 't') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
 static int decode_write_impl(const DecGeometry& g, uint8_t* d_out, u64 out_cap, void* d_ws, cudaStream_t stream) {
   const DecLayout L = dec_layout(g.slice_bits / 8);
   DecWorkspace ws = dec_bind(d_ws, L);
-  const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
-  GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, 0, stream, g, d_out, out_cap, ws);
+  if (use_thread_writer()) {
+    const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
+    GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, 0, stream, g, d_out, out_cap, ws);
+    return check_launch();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(sizeof(SmemWriteWarp))));
+    attr_set = true;
+  }
+  const unsigned blocks = unsigned((g.n_sub + kWriteWarps - 1) / kWriteWarps);
+  GH_LAUNCH(dec_write_warp_kernel, blocks, kWriteWarps * 32, sizeof(SmemWriteWarp), stream, g, d_out, out_cap, ws);
   return check_launch();
 }
 

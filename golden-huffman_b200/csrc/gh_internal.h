@@ -19,7 +19,11 @@ namespace gh {
 //                      0 = the first codeword does not fit or is the end mark. Used where only counts matter.
 //   lutW  2^13 x u32   up to 3 whole codewords in 13 bits: total length | count << 4 | symbols << 8 (first symbol
 //                      in the lowest byte), 0 = first codeword does not fit or is the end mark.
+//   lutP  2^12 x u32   one or two whole codewords in 12 bits, with the first length kept so a step can stop after
+//                      the first: total length | count << 4 | first length << 6 | symbol 1 << 16 | symbol 2 << 24,
+//                      0 = first codeword does not fit or is the end mark. Used by the warp-cooperative writer.
 constexpr int kLut1Bits = 12;
+constexpr int kLutPBits = 12;
 constexpr int kLutCBits = 15;
 constexpr int kLutWBits = 13;
 constexpr int kLutWMaxSyms = 3;

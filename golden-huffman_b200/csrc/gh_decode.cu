@@ -667,12 +667,12 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   u64 acc = 0, held = 0;
   u32 nacc = 0;  // symbols in acc (0..7 between iterations), first symbol in the lowest byte
   bool have_held = false;
-  auto emit = [&](u32 syms, u32 n) {
+  auto emit = [&](u64 syms, u32 n) {  // n <= 6 symbols, first in the lowest byte
     const u32 sh = nacc * 8;
-    acc |= u64(syms) << sh;
+    acc |= syms << sh;
     nacc += n;
     if (nacc >= 8) {
-      const u64 spill = sh > 40 ? u64(syms) >> (64 - sh) : 0ull;  // bytes that did not fit
+      const u64 spill = sh ? syms >> (64 - sh) : 0ull;  // bytes that did not fit
       if (have_held) {
         *reinterpret_cast<uint4*>(dst) = make_uint4(u32(held), u32(held >> 32), u32(acc), u32(acc >> 32));
         dst += 16;
@@ -719,9 +719,11 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         avail -= int(drop);
         if (avail < 32) push();
       }
-      while (remaining >= u32(kLutWMaxSyms) && vnext < vend) {
-        const u32 win = u32(buf >> 32);
-        const u32 e = s.lutW[win >> (32 - kLutWBits)];
+      // two lookups per iteration, one refill check and one retirement check for both: a table hit needs at most
+      // 13 valid bits, so after the first hit (>= 32 - 13 = 19 bits left) the second can go ahead unrefilled
+      while (remaining >= 2u * kLutWMaxSyms && vnext < vend) {
+        u32 win = u32(buf >> 32);
+        u32 e = s.lutW[win >> (32 - kLutWBits)];
         u32 n, syms;
         if (e) {
           len = e & 15u;
@@ -735,9 +737,27 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         pos += len;
         buf <<= len;
         avail -= int(len);
-        remaining -= n;
+        if (avail < int(kLutWBits)) push();  // only after a long codeword
+        win = u32(buf >> 32);
+        e = s.lutW[win >> (32 - kLutWBits)];
+        u32 n2, syms2;
+        if (e) {
+          len = e & 15u;
+          n2 = (e >> 4) & 3u;
+          syms2 = e >> 8;
+        } else {
+          if (avail < 32) push();
+          win = u32(buf >> 32);
+          decode_one(s.canon, s.lut1, win, sym, len);
+          n2 = 1;
+          syms2 = sym & 0xffu;
+        }
+        pos += len;
+        buf <<= len;
+        avail -= int(len);
         if (avail < 32) push();
-        emit(syms, n);
+        remaining -= n + n2;
+        emit(u64(syms) | (u64(syms2) << (8 * n)), n + n2);
       }
     }
   }
@@ -1130,19 +1150,23 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   return GH_OK;
 }
 
-static bool use_thread_writer() {  // GH_WRITE_KERNEL=thread selects the one-thread-per-subsequence writer (A/B runs)
-  static int cached = -1;
-  if (cached < 0) {
+// Two writers exist: one thread per subsequence (default) and one warp per subsequence (shared-memory staged,
+// coalesced I/O, but it decodes every piece 2.5 times; measured slower on B200 -- profiles/r1f -- and kept as
+// the starting point of the fine-grained pipeline planned in DESIGN.md). gh_debug_select_writer / the
+// GH_WRITE_KERNEL environment variable ("warp") pick the second one for A/B runs.
+static int g_writer = -1;  // 0 = thread, 1 = warp
+static bool use_warp_writer() {
+  if (g_writer < 0) {
     const char* e = getenv("GH_WRITE_KERNEL");
-    cached = (e && e[0] == 't') ? 1 : 0;
+    g_writer = (e && e[0] == 'w') ? 1 : 0;
   }
-  return cached == 1;
+  return g_writer == 1;
 }
 
 static int decode_write_impl(const DecGeometry& g, uint8_t* d_out, u64 out_cap, void* d_ws, cudaStream_t stream) {
   const DecLayout L = dec_layout(g.slice_bits / 8);
   DecWorkspace ws = dec_bind(d_ws, L);
-  if (use_thread_writer()) {
+  if (!use_warp_writer()) {
     const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
     GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, 0, stream, g, d_out, out_cap, ws);
     return check_launch();
@@ -1163,6 +1187,8 @@ static int decode_write_impl(const DecGeometry& g, uint8_t* d_out, u64 out_cap, 
 extern "C" {
 
 size_t gh_decode_workspace_bytes(uint64_t payload_bytes) { return gh::dec_layout(payload_bytes).total; }
+
+void gh_debug_select_writer(int warp_cooperative) { gh::g_writer = warp_cooperative ? 1 : 0; }
 
 int gh_decode_sync(const uint8_t* d_payload, uint64_t slice_bytes, uint64_t readable_bytes, const gh_code* code,
                    uint32_t entry_bit, int first_call, gh_shard_sync* result, void* d_workspace,

@@ -66,6 +66,9 @@ uint64_t gh_launch_count(void);
  * (and resets the counters). Returns the bytes written. Off by default. */
 void gh_profile_enable(int on);
 size_t gh_profile_fetch(char* buf, size_t cap);
+/* Diagnostics only: pick the experimental warp-cooperative K7 writer (non-zero) or the default
+ * thread-per-subsequence one (0) for A/B measurements. Output is identical either way. */
+void gh_debug_select_writer(int warp_cooperative);
 
 /* ------------------------------------------------------------------------------------------------
  * Host: code construction and the file header (microseconds; stays on the host by design)

@@ -55,13 +55,18 @@ __device__ __noinline__ uint4 load_ragged(const uint8_t* p, int cnt) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// OR the low `len` bits of `acc` (len in 1..64) into the staging bit string at bit position `pos`
+// OR the low `len` bits of `acc` (len in 1..64, higher bits of acc zero) into the staging bit string at bit
+// position `pos`. Worked from the value's last bit: it is shifted left by the free bits r that remain after it in
+// its last word, which gives the (up to) three words directly -- three shifts, no 64-bit left-justification.
 __device__ __forceinline__ void stage_bits(u32* stage, u32 pos, u64 acc, u32 len) {
-  const u64 v = acc << (64 - len);  // left-justified
-  const u32 w = pos >> 5, sh = pos & 31;
-  atomicOr(stage + w, u32(v >> 32) >> sh);
-  if (sh + len > 32) atomicOr(stage + w + 1, u32(v >> sh));
-  if (sh + len > 64) atomicOr(stage + w + 2, u32(v) << (32 - sh));
+  const u32 end = pos + len;           // one past the last bit
+  const u32 w_first = pos >> 5;
+  const u32 w_last = (end - 1) >> 5;
+  const u32 r = (0u - end) & 31u;      // free bits after the value inside word w_last
+  const u32 lo = u32(acc), hi = u32(acc >> 32);
+  atomicOr(stage + w_last, lo << r);
+  if (w_last > w_first) atomicOr(stage + w_last - 1, __funnelshift_l(lo, hi, r));
+  if (w_last > w_first + 1) atomicOr(stage + w_last - 2, r ? hi >> (32 - r) : 0u);
 }
 
 __device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
@@ -74,8 +79,8 @@ __global__ void __launch_bounds__(kEncThreads)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
               u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
   constexpr int kChunks = kEncBytesPerThread / kSymsPerChunk;
-  __shared__ u32 s_lut[GH_NSYM + 3];      // kSymsPerChunk == 4: (len << 16) | code ; else: code
-  __shared__ uint8_t s_len[GH_NSYM + 3];
+  __shared__ u64 s_lut[GH_NSYM + 3];      // (len << 32) | code: one LDS.64 yields both
+  __shared__ uint8_t s_len[GH_NSYM + 3];  // lengths alone, for the counting pass
   __shared__ u32 s_stage[2][kEncStageWords];
   __shared__ u32 s_warp_total[kEncSubTiles][kEncThreads / 32];
   __shared__ u32 s_carry[2];
@@ -85,7 +90,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);
   for (unsigned s = t; s < GH_NSYM; s += kEncThreads) {
-    s_lut[s] = kSymsPerChunk == 4 ? ((u32(table.length[s]) << 16) | table.codeword[s]) : table.codeword[s];
+    s_lut[s] = (u64(table.length[s]) << 32) | table.codeword[s];
     s_len[s] = table.length[s];
   }
   for (unsigned i = t; i < 2u * kEncStageWords; i += kEncThreads) (&s_stage[0][0])[i] = 0;
@@ -192,30 +197,27 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       u32* stage = s_stage[j & 1];
       {
         u32 pos = pos0[j];
-        const bool full = cnt[j] == kEncBytesPerThread;
+        if (cnt[j] == kEncBytesPerThread) {
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          u64 acc = 0;
-          u32 clen = 0;
+          for (int c = 0; c < kChunks; ++c) {
+            u64 acc = 0;
+            u32 clen = 0;
 #pragma unroll
-          for (int q = 0; q < kSymsPerChunk; ++q) {
-            const int k = c * kSymsPerChunk + q;
-            const u32 b = vec_byte(raw[j], k);
-            u32 code, len;
-            if (kSymsPerChunk == 4) {
-              const u32 e = s_lut[b];
-              code = e & 0xffffu;
-              len = e >> 16;
-            } else {
-              code = s_lut[b];
-              len = s_len[b];
+            for (int q = 0; q < kSymsPerChunk; ++q) {
+              const u64 e = s_lut[vec_byte(raw[j], c * kSymsPerChunk + q)];
+              const u32 len = u32(e >> 32);
+              acc = (acc << len) | u32(e);  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
+              clen += len;
             }
-            if (!full && k >= cnt[j]) len = 0, code = 0;  // ragged last vector of the input
-            acc = (acc << len) | code;  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
-            clen += len;
+            stage_bits(stage, pos, acc, clen);  // every byte value that occurs has a code: clen >= kSymsPerChunk
+            pos += clen;
           }
-          if (clen) stage_bits(stage, pos, acc, clen);
-          pos += clen;
+        } else {  // the ragged last vector of the input: symbol by symbol
+          for (int k = 0; k < cnt[j]; ++k) {
+            const u64 e = s_lut[vec_byte(raw[j], k)];
+            stage_bits(stage, pos, u32(e), u32(e >> 32));
+            pos += u32(e >> 32);
+          }
         }
         if (end_sub == j && eof_len_all) stage_bits(stage, pos, eof_code, eof_len_all);
       }

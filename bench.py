@@ -291,7 +291,8 @@ def main():
         alg = {  # algorithmic bytes per launch (DESIGN.md "roofline accounting")
             "hist_kernel": n, "encode_kernel": n + C_, "encode_stitch_kernel": 0,
             "dec_build_luts_kernel": 0, "dec_speculate_kernel": C_, "dec_sync_kernel": 0, "dec_tile_sum_kernel": 0, "dec_offsets_kernel": 0,
-            "dec_write_kernel": C_ + n,
+            "dec_write_kernel": C_ + n, "dec_fine_speculate_kernel": C_, "dec_fine_write_kernel": C_ + n,
+            "dec_sub_offsets_kernel": 0, "dec_locate_eof_kernel": 0,
         }
         def alg_bytes(name):
             return alg.get(name.split("<")[0], 0)

@@ -64,7 +64,7 @@ struct DecControl {  // device-resident, copied back to the host after each roun
   u32 exits_changed;  // subsequences whose exit moved in the last round
   u64 n_sub;
   u32 eof_prefix;     // symbols before the first end mark inside subsequence eof_index
-  u32 pad_;
+  u32 fine;           // 1: fine-grained pipeline (2 KiB segments, piece states valid)
 };
 
 struct DecWorkspace {
@@ -78,6 +78,7 @@ struct DecWorkspace {
   u32* neof;       // [n_sub]  end-mark codewords on each subsequence's path
   u32* eofpos;     // [n_sub]  symbols before the path's first end mark, kEofPosUnknown if it was not observed
   u64* out_off;    // [n_sub]  output offset of each subsequence's first symbol
+  u32* pieces;     // [32 * n_sub] fine pipeline only: state of each 64-byte piece
   u64* tile_sum;   // [n_tiles]
   u64* tile_base;  // [n_tiles]
 };
@@ -268,7 +269,7 @@ struct SmemSpeculate {
 };
 
 __global__ void __launch_bounds__(kDecThreads)
-dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
+dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   __shared__ SmemSpeculate s;
   load_canon(s.canon, ws.tables);
   for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
@@ -280,7 +281,17 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
   if (i >= g.n_sub) return;
   const u64 start = i * u64(g.sub_bytes) * 8;
   const u32 end = u32(sub_end_bits(g, i));
-  const u32 entry = (i == 0) ? g.entry0 : 0u;
+  u32 entry = (i == 0) ? g.entry0 : 0u;
+  u32 old_exit = 0xffffffffu;
+  if (respeculate) {
+    // synchronisation round by re-walking: for codes that need about a whole subsequence to re-synchronise the
+    // lockstep walk of K5b buys nothing (the paths rarely meet early) and costs two slow walks; walking the
+    // corrected path once with this kernel's bulk loop is several times cheaper. Same fixed-point iteration.
+    const u64 mine = ld_volatile_u64(ws.sub + i);
+    if (i > 0) entry = st_exit(ld_volatile_u64(ws.sub + i - 1));
+    if (entry == st_entry(mine)) return;
+    old_exit = st_exit(mine);
+  }
   u32 pos = entry, count = 0, neof = 0, first_eof = kNoEof;
   const bool bulk = end >= u32(kLutCBits);
   const u32 last = end - u32(kLutCBits);  // multi-codeword steps are allowed while pos <= last (only used if bulk)
@@ -376,9 +387,13 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws) {
     pos += len;
     r.consume(len);
   }
-  ws.sub[i] = pack_state(count, entry, pos - end, neof != 0);
   ws.neof[i] = neof;
   ws.eofpos[i] = first_eof;  // codewords before the first end mark are all symbols
+  st_volatile_u64(ws.sub + i, pack_state(count, entry, pos - end, neof != 0));
+  if (respeculate && (pos - end) != old_exit) {
+    ws.ctl->changed = 1u;
+    atomicAdd(&ws.ctl->exits_changed, 1u);
+  }
 }
 
 // ---- K5b: one synchronisation round ------------------------------------------------------------------------
@@ -811,34 +826,48 @@ dec_sub_offsets_kernel(DecGeometry g, DecWorkspace ws) {
   if (i < g.n_sub) ws.out_off[i] = ws.tile_base[blockIdx.x] + warp_base + (incl - count);
 }
 
-// ---- K7 (warp-cooperative): one warp per subsequence, shared-memory staging on both sides ---------------------
-// A subsequence's exact entry and symbol count are known, but a single thread walking it pays for every per-lane
-// event (refill, reload, retiring output registers) on every iteration, because 32 lanes are never in step.
-// Here a warp takes the subsequence in 2 KiB segments instead:
+// ---- fine-grained pipeline: one warp per 2 KiB segment, 64-byte pieces, shared-memory staging -------------------
+// For codes that re-synchronise within a few codewords (anything but near-fixed-length codes) the subsequence is
+// fixed at 2 KiB and handled by a warp:
 //   stage   coalesced 128-bit loads of the segment into shared memory (stream order, one pad word per 16 so that
-//           the 32 lanes' pieces start in 32 different banks);
-//   pass A  lane l walks the 64-byte piece l of the segment from its start, counting codewords (lane 0 starts at
-//           the exact entry): bit-addressed windows straight from shared memory, no refill state at all;
-//   fix-up  lanes pass their exits to the right (shuffle); a lane whose assumed entry was wrong walks old and new
-//           path in lockstep until they meet (a few codewords) and patches its count; repeated until no exit moves
-//           -- the same fixed-point argument as K5b, inside a warp and without touching memory;
-//   scan    warp scan of the counts -> each lane's position in the segment's output;
-//   pass B  lanes decode again from their exact entries and store symbols as bytes into a shared output window;
-//   copy    the window leaves as coalesced 128-bit stores (its phase in shared memory equals the destination's).
-// Every lane does the same thing in every iteration; the only divergence left is the trip count of the piece loop.
-constexpr int kWriteWarps = 16;
+//           the 32 lanes' pieces start in 32 different banks); every later bit access is a bit-addressed window
+//           out of shared memory -- no refill state, so lanes stay in step;
+//   K5a'    lane l walks 64-byte piece l from its first bit (lane 0 from the segment's entry) counting codewords;
+//           lanes then pass their exits to the right (shuffle) and a lane whose assumed entry was wrong walks old
+//           and new path in lockstep until they meet (a few codewords) and patches its count -- repeated until no
+//           exit moves: the fixed-point argument of K5b inside a warp, without touching memory. The piece states
+//           (count, exit, end marks) are stored, 4 bytes per 64-byte piece, plus the usual per-subsequence state,
+//           so K5b/K6 run unchanged on the segments.
+//   K7'     re-stages the segment, re-validates the stored piece states against the segment's now-exact entry (lane
+//           0 walks a few codewords in the common case), scans the counts, and every lane decodes its piece ONCE,
+//           storing symbols as bytes into a shared output window that leaves as coalesced 128-bit stores.
+// (A writer that re-derived the piece entries itself -- 2.5 decode passes per piece -- measured 2x slower than the
+//  thread-per-subsequence writer: profiles/r1f. Storing the piece states removes those passes.)
+constexpr int kFineWarps = 16;
+constexpr u32 kFineSubBytes = 2048;
 constexpr u32 kPieceBits = 512;
-constexpr u32 kSegBits = 32 * kPieceBits;             // 2 KiB of payload per segment
-constexpr u32 kSegStageVecs = kSegBits / 128 + 3;     // + alignment slack (entry < 128 bits) + look-ahead
+constexpr u32 kSegBits = 32 * kPieceBits;
+constexpr u32 kSegStageVecs = kSegBits / 128 + 3;  // + look-ahead for windows that start in the last piece
 constexpr u32 kSegStageWords = kSegStageVecs * 4;
 constexpr u32 kSegPaddedWords = kSegStageWords + kSegStageWords / 16 + 1;
-constexpr u32 kOutWindow = 3072;                      // symbols per copy-out window (multiple of 16)
+constexpr u32 kOutWindow = 3072;  // symbols per copy-out window (multiple of 16)
 
-struct SmemWriteWarp {
+// piece state: [9:0] codewords  [14:10] exit  [24:15] end marks among the codewords
+__device__ __forceinline__ u32 pack_piece(u32 cnt, u32 exit, u32 neof) { return cnt | (exit << 10) | (neof << 15); }
+__device__ __forceinline__ u32 pc_count(u32 p) { return p & 1023u; }
+__device__ __forceinline__ u32 pc_exit(u32 p) { return (p >> 10) & 31u; }
+__device__ __forceinline__ u32 pc_neof(u32 p) { return (p >> 15) & 1023u; }
+
+struct SmemFineSpec {
   SmemCanon canon;
   u32 lutP[1 << kLutPBits];
-  u32 in[kWriteWarps][kSegPaddedWords];
-  __align__(16) uint8_t out[kWriteWarps][kOutWindow + 32];
+  u32 in[kFineWarps][kSegPaddedWords];
+};
+struct SmemFineWrite {
+  SmemCanon canon;
+  u32 lutP[1 << kLutPBits];
+  u32 in[kFineWarps][kSegPaddedWords];
+  __align__(16) uint8_t out[kFineWarps][kOutWindow + 32];
 };
 
 __device__ __forceinline__ u32 seg_window(const u32* sin, u32 pos) {
@@ -847,151 +876,214 @@ __device__ __forceinline__ u32 seg_window(const u32* sin, u32 pos) {
   return __funnelshift_l(sin[b], sin[a], pos & 31);
 }
 
-// one step of a path inside a piece: one or two whole codewords, never a second one once the first reaches p_end
-__device__ __forceinline__ void piece_step(const SmemWriteWarp& s, const u32* sin, u32 p_end, u32& pos, u32& cnt) {
+// coalesced copy of a segment's vectors into the padded shared layout, stream order
+__device__ __forceinline__ void stage_segment(const DecGeometry& g, u64 vec0, u32* sin, unsigned lane) {
+  const u64 full_vecs = g.readable >> 4;
+  for (u32 k = lane; k < kSegStageVecs; k += 32) {
+    const u64 v = vec0 + k;
+    const uint4 q = v < full_vecs ? ldg128(reinterpret_cast<const uint4*>(g.payload) + v)
+                                  : fetch_tail(g.payload, g.readable, v);
+    const u32 j = 4 * k, base = j + (j >> 4);
+    sin[base] = be32(q.x);
+    sin[base + 1] = be32(q.y);
+    sin[base + 2] = be32(q.z);
+    sin[base + 3] = be32(q.w);
+  }
+}
+
+// one step of a path inside a piece: one or two whole codewords (never a second one once the first reaches p_end)
+__device__ __forceinline__ void piece_step(const SmemCanon& canon, const u32* lutP, const u32* sin, u32 p_end, u32& pos,
+                                           u32& cnt, u32& neof) {
   const u32 win = seg_window(sin, pos);
-  const u32 e = s.lutP[win >> (32 - kLutPBits)];
+  const u32 e = lutP[win >> (32 - kLutPBits)];
   if (e) {
     const u32 len1 = (e >> 6) & 15u;
     const bool both = ((e >> 4) & 3u) == 2u && pos + len1 < p_end;
     pos += both ? (e & 15u) : len1;
     cnt += both ? 2u : 1u;
-  } else {  // longer than 12 bits, or the end mark (runs through like any codeword; counts are trimmed later)
+  } else {  // longer than 12 bits, or the end mark (a path runs through it like through any codeword)
     u32 sym, len;
-    canon_search(s.canon, win, s.canon.min_len, sym, len);
+    canon_search(canon, win, canon.min_len, sym, len);
     pos += len;
     ++cnt;
+    neof += sym == u32(GH_EOF_SYMBOL);
   }
 }
 
-__global__ void __launch_bounds__(kWriteWarps * 32)
-dec_write_warp_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
+// Warp-level fixed point over the 32 pieces of a staged segment. On entry every lane holds the state (entry, cnt,
+// exit, neof) of the path it last walked; lane 0's entry must become `seg_entry`, lane l's the left exit.
+__device__ __forceinline__ void fix_pieces(const SmemCanon& canon, const u32* lutP, const u32* sin, unsigned lane,
+                                           u32 p_begin, u32 p_end, u32 seg_entry, u32& entry, u32& cnt, u32& exit,
+                                           u32& neof) {
+  while (true) {
+    const u32 left_exit = __shfl_up_sync(0xffffffffu, exit, 1);
+    const u32 want = lane == 0 ? seg_entry : p_begin + left_exit;
+    bool moved = false;
+    if (want != entry) {
+      u32 pa = entry, pb = want, sa = 0, sb = 0, ea = 0, eb = 0;
+      bool merged = false;
+      while (pb < p_end) {
+        if (pa == pb) {
+          merged = true;
+          break;
+        }
+        if (pa < pb) piece_step(canon, lutP, sin, p_end, pa, sa, ea);
+        else piece_step(canon, lutP, sin, p_end, pb, sb, eb);
+      }
+      if (merged) {  // counts are additive: the rest of the stored path is the rest of the new one
+        cnt = sb + (cnt - sa);
+        neof = eb + (neof - ea);
+      } else {
+        const u32 new_exit = pb >= p_end ? pb - p_end : 0u;
+        cnt = sb;
+        neof = eb;
+        moved = new_exit != exit;
+        exit = new_exit;
+      }
+      entry = want;
+    }
+    if (!__any_sync(0xffffffffu, moved)) break;
+  }
+}
+
+// ---- K5a' ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFineWarps * 32)
+dec_fine_speculate_kernel(DecGeometry g, DecWorkspace ws) {
   GH_DYNAMIC_SMEM(smem_raw);
-  SmemWriteWarp& s = *reinterpret_cast<SmemWriteWarp*>(smem_raw);
+  SmemFineSpec& s = *reinterpret_cast<SmemFineSpec*>(smem_raw);
   load_canon(s.canon, ws.tables);
-  for (unsigned k = threadIdx.x; k < (1u << kLutPBits) / 4; k += kWriteWarps * 32)
+  for (unsigned k = threadIdx.x; k < (1u << kLutPBits) / 4; k += kFineWarps * 32)
     reinterpret_cast<uint4*>(s.lutP)[k] = reinterpret_cast<const uint4*>(ws.lutP)[k];
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const u64 i = u64(blockIdx.x) * kWriteWarps + wib;
+  const u64 i = u64(blockIdx.x) * kFineWarps + wib;
+  if (i >= g.n_sub) return;  // warp-uniform
+  u32* sin = s.in[wib];
+  const u32 seg_end = u32(sub_end_bits(g, i));  // < kSegBits only for the last segment
+  stage_segment(g, i * (kFineSubBytes / 16), sin, lane);
+  __syncwarp();
+  const u32 seg_entry = (i == 0) ? g.entry0 : 0u;
+  const u32 p_begin = lane * kPieceBits < seg_end ? lane * kPieceBits : seg_end;
+  const u32 p_end = (lane + 1) * kPieceBits < seg_end ? (lane + 1) * kPieceBits : seg_end;
+  u32 entry = lane == 0 ? seg_entry : p_begin;
+  u32 pos = entry, cnt = 0, neof = 0;
+  while (pos < p_end) piece_step(s.canon, s.lutP, sin, p_end, pos, cnt, neof);
+  u32 exit = pos >= p_end ? pos - p_end : 0u;
+  fix_pieces(s.canon, s.lutP, sin, lane, p_begin, p_end, seg_entry, entry, cnt, exit, neof);
+  ws.pieces[i * 32 + lane] = pack_piece(cnt, exit, neof);
+  const u32 seg_cnt = warp_sum(cnt), seg_neof = warp_sum(neof);
+  if (lane == 31) {
+    ws.sub[i] = pack_state(seg_cnt, seg_entry, exit, seg_neof != 0);
+    ws.neof[i] = seg_neof;
+    ws.eofpos[i] = seg_neof ? kEofPosUnknown : kNoEof;  // K6 locates the mark if this segment turns out to end the stream
+  }
+}
+
+// ---- K7' ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFineWarps * 32)
+dec_fine_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
+  GH_DYNAMIC_SMEM(smem_raw);
+  SmemFineWrite& s = *reinterpret_cast<SmemFineWrite*>(smem_raw);
+  load_canon(s.canon, ws.tables);
+  for (unsigned k = threadIdx.x; k < (1u << kLutPBits) / 4; k += kFineWarps * 32)
+    reinterpret_cast<uint4*>(s.lutP)[k] = reinterpret_cast<const uint4*>(ws.lutP)[k];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u64 i = u64(blockIdx.x) * kFineWarps + wib;
+  if (i >= g.n_sub) return;  // warp-uniform
+  const u32 eof_index = ws.ctl->eof_index;
+  if (i > u64(eof_index)) return;
+  const u64 st = ws.sub[i];
+  u32 remaining = i == u64(eof_index) ? ws.ctl->eof_prefix : st_count(st);
+  const u64 o = ws.out_off[i];
+  if (o >= out_cap) return;
+  if (u64(remaining) > out_cap - o) remaining = u32(out_cap - o);
+  if (remaining == 0) return;
   u32* sin = s.in[wib];
   uint8_t* sout = s.out[wib];
-
-  // everything below is warp-uniform control flow around warp-synchronous phases
-  u32 remaining = 0;
-  u64 o = 0, bitpos = 0;
-  if (i < g.n_sub) {
-    const u32 eof_index = ws.ctl->eof_index;
-    const u64 st = ws.sub[i];
-    if (i <= u64(eof_index)) remaining = i == u64(eof_index) ? ws.ctl->eof_prefix : st_count(st);
-    o = ws.out_off[i];
-    if (o >= out_cap) remaining = 0;
-    else if (u64(remaining) > out_cap - o) remaining = u32(out_cap - o);
-    bitpos = i * u64(g.sub_bytes) * 8 + st_entry(st);
-  }
-  const u64 full_vecs = g.readable >> 4;
-  while (remaining > 0) {
-    // ---- stage the segment that starts at the 16-byte vector holding `bitpos` ------------------------------
-    const u64 vec0 = bitpos >> 7;
-    const u32 first = u32(bitpos & 127);  // the exact entry, as a bit offset into the staged words
-    for (u32 k = lane; k < kSegStageVecs; k += 32) {
-      const u64 v = vec0 + k;
-      const uint4 q = v < full_vecs ? ldg128(reinterpret_cast<const uint4*>(g.payload) + v)
-                                    : fetch_tail(g.payload, g.readable, v);
-      const u32 j = 4 * k, base = j + (j >> 4);
-      sin[base] = be32(q.x);
-      sin[base + 1] = be32(q.y);
-      sin[base + 2] = be32(q.z);
-      sin[base + 3] = be32(q.w);
+  const u32 seg_end = u32(sub_end_bits(g, i));
+  stage_segment(g, i * (kFineSubBytes / 16), sin, lane);
+  // stored piece states describe the paths K5a' settled on with the speculative segment entry
+  const u32 ps = ws.pieces[i * 32 + lane];
+  u32 cnt = pc_count(ps), exit = pc_exit(ps), neof = pc_neof(ps);
+  const u32 p_begin = lane * kPieceBits < seg_end ? lane * kPieceBits : seg_end;
+  const u32 p_end = (lane + 1) * kPieceBits < seg_end ? (lane + 1) * kPieceBits : seg_end;
+  const u32 left_exit = __shfl_up_sync(0xffffffffu, exit, 1);
+  u32 entry = lane == 0 ? ((i == 0) ? g.entry0 : 0u) : p_begin + left_exit;
+  __syncwarp();
+  // re-validate against the exact segment entry (usually lane 0 walks a few codewords and nothing else moves)
+  fix_pieces(s.canon, s.lutP, sin, lane, p_begin, p_end, st_entry(st), entry, cnt, exit, neof);
+  const u32 incl = warp_inclusive_scan(cnt, lane);
+  const u32 prefix = incl - cnt;
+  const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+  const u32 seg_syms = total < remaining ? total : remaining;
+  const u32 my_end = prefix >= seg_syms ? prefix : (incl < seg_syms ? incl : seg_syms);  // my symbols: [prefix, my_end)
+  const u32 a0 = u32(reinterpret_cast<uintptr_t>(out + o) & 15);  // window phase == destination phase
+  u32 idx = prefix;  // segment-relative index of my next symbol
+  u32 pos = entry;
+  for (u32 wbase = 0; wbase < seg_syms; wbase += kOutWindow) {
+    const u32 wend = wbase + kOutWindow < seg_syms ? wbase + kOutWindow : seg_syms;
+    const u32 lim = my_end < wend ? my_end : wend;
+    uint8_t* slot = sout + a0 - wbase;  // slot[idx] is where symbol idx of the segment goes
+    while (idx < lim) {
+      const u32 win = seg_window(sin, pos);
+      const u32 e = s.lutP[win >> (32 - kLutPBits)];
+      if (e) {
+        const bool both = ((e >> 4) & 3u) == 2u && idx + 1 < lim;
+        slot[idx] = uint8_t(e >> 16);
+        if (both) slot[idx + 1] = uint8_t(e >> 24);
+        pos += both ? (e & 15u) : ((e >> 6) & 15u);
+        idx += both ? 2u : 1u;
+      } else {
+        u32 sym, len;
+        canon_search(s.canon, win, s.canon.min_len, sym, len);
+        slot[idx] = uint8_t(sym);
+        pos += len;
+        ++idx;
+      }
     }
     __syncwarp();
-    // ---- pass A: count the codewords of my piece, starting at its first bit (lane 0: at the exact entry) ----
-    const u32 p_begin = first + lane * kPieceBits, p_end = p_begin + kPieceBits;
-    u32 entry = p_begin, cnt = 0, pos = p_begin;
-    while (pos < p_end) piece_step(s, sin, p_end, pos, cnt);
-    u32 exit = pos - p_end;
-    // ---- fix-up: entries from the left neighbours' exits, until no exit moves ------------------------------
-    while (true) {
-      const u32 left_exit = __shfl_up_sync(0xffffffffu, exit, 1);
-      const u32 want = lane == 0 ? entry : p_begin + left_exit;
-      bool moved = false;
-      if (want != entry) {
-        u32 pa = entry, pb = want, sa = 0, sb = 0;
-        bool merged = false;
-        while (pb < p_end) {
-          if (pa == pb) {
-            merged = true;
-            break;
-          }
-          if (pa < pb) piece_step(s, sin, p_end, pa, sa);
-          else piece_step(s, sin, p_end, pb, sb);
-        }
-        if (merged) {
-          cnt = sb + (cnt - sa);
-        } else {
-          cnt = sb;
-          moved = (pb - p_end) != exit;
-          exit = pb - p_end;
-        }
-        entry = want;
-      }
-      if (!__any_sync(0xffffffffu, moved)) break;
-    }
-    // ---- scan, trim to what this subsequence still owes ---------------------------------------------------------
-    const u32 incl = warp_inclusive_scan(cnt, lane);
-    const u32 prefix = incl - cnt;
-    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-    const u32 seg_syms = total < remaining ? total : remaining;
-    const u32 my_end = prefix >= seg_syms ? prefix : (incl < seg_syms ? incl : seg_syms);  // my symbols: [prefix, my_end)
-    const u32 last_exit = __shfl_sync(0xffffffffu, exit, 31);
-    // ---- pass B + copy-out, one output window at a time -------------------------------------------------------
-    const u32 a0 = u32(reinterpret_cast<uintptr_t>(out + o) & 15);  // window phase == destination phase
-    u32 idx = prefix;  // segment-relative index of my next symbol
-    pos = entry;
-    for (u32 wbase = 0; wbase < seg_syms; wbase += kOutWindow) {
-      const u32 wend = wbase + kOutWindow < seg_syms ? wbase + kOutWindow : seg_syms;
-      const u32 lim = my_end < wend ? my_end : wend;
-      uint8_t* slot = sout + a0 - wbase;  // slot[idx] is where symbol idx of the segment goes
-      while (idx < lim) {
-        const u32 win = seg_window(sin, pos);
-        const u32 e = s.lutP[win >> (32 - kLutPBits)];
-        if (e) {
-          const bool both = ((e >> 4) & 3u) == 2u && idx + 1 < lim;
-          slot[idx] = uint8_t(e >> 16);
-          if (both) slot[idx + 1] = uint8_t(e >> 24);
-          pos += both ? (e & 15u) : ((e >> 6) & 15u);
-          idx += both ? 2u : 1u;
-        } else {
-          u32 sym, len;
-          canon_search(s.canon, win, s.canon.min_len, sym, len);
-          slot[idx] = uint8_t(sym);
-          pos += len;
-          ++idx;
-        }
-      }
-      __syncwarp();
-      const u32 m = wend - wbase;  // bytes in this window, at sout[a0 .. a0 + m)
-      uint8_t* dst = out + o + wbase;
-      const u32 head = a0 ? ((16 - a0) < m ? (16 - a0) : m) : 0u;
-      if (lane < head) dst[lane] = sout[a0 + lane];
-      const u32 nvec = (m - head) >> 4;
-      const uint4* src4 = reinterpret_cast<const uint4*>(sout + a0 + head);
-      uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
-      for (u32 k = lane; k < nvec; k += 32) dst4[k] = src4[k];
-      const u32 done = head + (nvec << 4);
-      if (lane < m - done) dst[done + lane] = sout[a0 + done + lane];
-      __syncwarp();
-    }
-    // ---- next segment starts at the boundary after the last piece ---------------------------------------------
-    bitpos = (vec0 << 7) + first + kSegBits + last_exit;
-    remaining -= seg_syms;
-    o += seg_syms;
+    const u32 m = wend - wbase;  // bytes in this window, at sout[a0 .. a0 + m)
+    uint8_t* dst = out + o + wbase;
+    const u32 head = a0 ? ((16 - a0) < m ? (16 - a0) : m) : 0u;
+    if (lane < head) dst[lane] = sout[a0 + lane];
+    const u32 nvec = (m - head) >> 4;
+    const uint4* src4 = reinterpret_cast<const uint4*>(sout + a0 + head);
+    uint4* dst4 = reinterpret_cast<uint4*>(dst + head);
+    for (u32 k = lane; k < nvec; k += 32) dst4[k] = src4[k];
+    const u32 done = head + (nvec << 4);
+    if (lane < m - done) dst[done + lane] = sout[a0 + done + lane];
+    __syncwarp();
   }
 }
 
 // ---- host orchestration -------------------------------------------------------------------------------
+// Pipeline choice: 0 = automatic (fine-grained for codes that re-synchronise quickly, coarse otherwise),
+// 1 = always coarse (one thread per subsequence), 2 = always fine. gh_debug_select_writer / GH_DECODE_PIPELINE
+// ("coarse" / "fine") override the automatic choice for A/B runs; the output is identical either way.
+static int g_pipeline = -1;
+static int pipeline_choice() {
+  if (g_pipeline < 0) {
+    const char* e = getenv("GH_DECODE_PIPELINE");
+    g_pipeline = (e && e[0] == 'c') ? 1 : (e && e[0] == 'f') ? 2 : 0;
+  }
+  return g_pipeline;
+}
+
+static int set_fine_attrs() {
+  static bool done = false;
+  if (!done) {
+    GH_CUDA_TRY(cudaFuncSetAttribute(dec_fine_speculate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(sizeof(SmemFineSpec))));
+    GH_CUDA_TRY(cudaFuncSetAttribute(dec_fine_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(sizeof(SmemFineWrite))));
+    done = true;
+  }
+  return GH_OK;
+}
+
 struct DecLayout {
-  size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_tile_sum, off_tile_base, total;
+  size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_pieces, off_tile_sum, off_tile_base, total;
 };
 
 static DecLayout dec_layout(u64 slice_bytes) {
@@ -1009,7 +1101,8 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_neof = L.off_sub + up(size_t(max_sub) * 8);
   L.off_eofpos = L.off_neof + up(size_t(max_sub) * 4);
   L.off_out_off = L.off_eofpos + up(size_t(max_sub) * 4);
-  L.off_tile_sum = L.off_out_off + up(size_t(max_sub) * 8);
+  L.off_pieces = L.off_out_off + up(size_t(max_sub) * 8);
+  L.off_tile_sum = L.off_pieces + up((size_t(slice_bytes) / kFineSubBytes + 2) * 32 * 4);
   L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
   L.total = L.off_tile_base + up(size_t(max_tiles) * 8);
   return L;
@@ -1028,6 +1121,7 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   w.neof = reinterpret_cast<u32*>(p + L.off_neof);
   w.eofpos = reinterpret_cast<u32*>(p + L.off_eofpos);
   w.out_off = reinterpret_cast<u64*>(p + L.off_out_off);
+  w.pieces = reinterpret_cast<u32*>(p + L.off_pieces);
   w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
   w.tile_base = reinterpret_cast<u64*>(p + L.off_tile_base);
   return w;
@@ -1057,7 +1151,7 @@ static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* 
 
 static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 readable, const gh_code* code, u32 entry_bit,
                             int first_call, gh_shard_sync* result, void* d_ws, size_t ws_bytes, cudaStream_t stream,
-                            DecGeometry* geom_out) {
+                            DecGeometry* geom_out, bool* fine_out = nullptr) {
   if (!d_payload || !code || !d_ws) return GH_ERR_ARG;
   if (slice_bytes == 0) return GH_ERR_NO_EOF;
   if ((reinterpret_cast<uintptr_t>(d_payload) & 15) || (reinterpret_cast<uintptr_t>(d_ws) & 255)) return GH_ERR_ARG;
@@ -1071,6 +1165,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   g.slice_bits = slice_bytes * 8;
   g.readable = readable;
   g.entry0 = entry_bit;
+  bool fine = false;
 
   if (first_call) {
     DecodeTables tables;
@@ -1079,15 +1174,19 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     GH_CUDA_TRY(cudaMemcpyAsync(const_cast<DecodeTables*>(ws.tables), &tables, sizeof(tables), cudaMemcpyHostToDevice, stream));
     GH_LAUNCH(dec_build_luts_kernel, (1u << kLutCBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
               const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW), const_cast<u32*>(ws.lutP));
+    const bool slow_code = code->max_len - code->min_len <= 1;
+    fine = pipeline_choice() == 2 || (pipeline_choice() == 0 && !slow_code);
     g.sub_bytes = choose_sub_bytes(slice_bytes);
     // near-fixed-length codes (all lengths within one bit: uniform-looking bytes) re-synchronise only when one of
     // the rare longer codewords shifts the phase; start them 4x coarser (measured on uniform bytes: the paths need
     // ~5.7k symbols on average to meet)
-    if (code->max_len - code->min_len <= 1 && u64(g.sub_bytes) * 4 <= kMaxSubBytes) g.sub_bytes *= 4;
+    if (slow_code && u64(g.sub_bytes) * 4 <= kMaxSubBytes) g.sub_bytes *= 4;
+    if (fine) g.sub_bytes = kFineSubBytes;
   } else {
     GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
     GH_CUDA_TRY(cudaStreamSynchronize(stream));
     g.sub_bytes = h_ctl.sub_bytes;
+    fine = h_ctl.fine != 0;
     if (g.sub_bytes < kMinSubBytes || (g.sub_bytes % kMinSubBytes)) return GH_ERR_ARG;
   }
   // Synchronisation rounds until a clean one. Round k makes subsequences 0..k exact whatever the data, so this
@@ -1099,11 +1198,19 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   // instead of dozens of rounds.
   u32 rounds = 0;
   bool speculate = first_call != 0, coarsened = false;
+  bool rewalk = code->max_len - code->min_len <= 1;  // near-fixed-length codes: see dec_speculate_kernel
   while (true) {
     g.n_sub = (slice_bytes + g.sub_bytes - 1) / g.sub_bytes;
     const unsigned blocks = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
     if (speculate) {
-      GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws);
+      if (fine) {
+        int rc = set_fine_attrs();
+        if (rc != GH_OK) return rc;
+        GH_LAUNCH(dec_fine_speculate_kernel, unsigned((g.n_sub + kFineWarps - 1) / kFineWarps), kFineWarps * 32,
+                  sizeof(SmemFineSpec), stream, g, ws);
+      } else {
+        GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws, 0);
+      }
       int rc = check_launch();
       if (rc != GH_OK) return rc;
     }
@@ -1113,14 +1220,25 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
       h_ctl.eof_index = kNoEof;
       h_ctl.sub_bytes = g.sub_bytes;
       h_ctl.n_sub = g.n_sub;
+      h_ctl.fine = fine ? 1u : 0u;
       GH_CUDA_TRY(cudaMemcpyAsync(ws.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, stream));
-      GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
+      if (rewalk && !fine) GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws, 1);
+      else GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
       int rc = check_launch();
       if (rc != GH_OK) return rc;
       GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
       GH_CUDA_TRY(cudaStreamSynchronize(stream));
       ++rounds;
       if (!h_ctl.changed) break;
+      // more than a tenth of the exits moved: the paths do not meet early with this code, stop trying to
+      if (u64(h_ctl.exits_changed) * 10 > g.n_sub) {
+        rewalk = true;
+        if (fine && pipeline_choice() == 0 && level_round == 0 && speculate) {  // misjudged: redo it coarsely
+          fine = false;
+          coarsen = true;
+          break;
+        }
+      }
       // coarsen (once, and only while the grid still fills the GPU) when more than half of the exits moved in
       // the first round: ~log(n_sub)/log(1/fraction) rounds are ahead, and a round costs one subsequence walk
       if (level_round == 0 && speculate && !coarsened && u64(h_ctl.exits_changed) * 2 > g.n_sub &&
@@ -1132,6 +1250,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     }
     if (!coarsen) break;
     coarsened = true;
+    if (g.sub_bytes == kFineSubBytes && !fine) g.sub_bytes = choose_sub_bytes(slice_bytes);
     u64 bigger = u64(g.sub_bytes) * 4;
     g.sub_bytes = u32(bigger > kMaxSubBytes ? kMaxSubBytes : bigger);
     speculate = true;
@@ -1147,38 +1266,23 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     result->sub_bytes = g.sub_bytes;
   }
   if (geom_out) *geom_out = g;
+  if (fine_out) *fine_out = fine;
   return GH_OK;
 }
 
-// Two writers exist: one thread per subsequence (default) and one warp per subsequence (shared-memory staged,
-// coalesced I/O, but it decodes every piece 2.5 times; measured slower on B200 -- profiles/r1f -- and kept as
-// the starting point of the fine-grained pipeline planned in DESIGN.md). gh_debug_select_writer / the
-// GH_WRITE_KERNEL environment variable ("warp") pick the second one for A/B runs.
-static int g_writer = -1;  // 0 = thread, 1 = warp
-static bool use_warp_writer() {
-  if (g_writer < 0) {
-    const char* e = getenv("GH_WRITE_KERNEL");
-    g_writer = (e && e[0] == 'w') ? 1 : 0;
-  }
-  return g_writer == 1;
-}
-
-static int decode_write_impl(const DecGeometry& g, uint8_t* d_out, u64 out_cap, void* d_ws, cudaStream_t stream) {
+static int decode_write_impl(const DecGeometry& g, bool fine, uint8_t* d_out, u64 out_cap, void* d_ws,
+                             cudaStream_t stream) {
   const DecLayout L = dec_layout(g.slice_bits / 8);
   DecWorkspace ws = dec_bind(d_ws, L);
-  if (!use_warp_writer()) {
+  if (fine) {
+    int rc = set_fine_attrs();
+    if (rc != GH_OK) return rc;
+    const unsigned blocks = unsigned((g.n_sub + kFineWarps - 1) / kFineWarps);
+    GH_LAUNCH(dec_fine_write_kernel, blocks, kFineWarps * 32, sizeof(SmemFineWrite), stream, g, d_out, out_cap, ws);
+  } else {
     const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
     GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, 0, stream, g, d_out, out_cap, ws);
-    return check_launch();
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     int(sizeof(SmemWriteWarp))));
-    attr_set = true;
-  }
-  const unsigned blocks = unsigned((g.n_sub + kWriteWarps - 1) / kWriteWarps);
-  GH_LAUNCH(dec_write_warp_kernel, blocks, kWriteWarps * 32, sizeof(SmemWriteWarp), stream, g, d_out, out_cap, ws);
   return check_launch();
 }
 
@@ -1188,7 +1292,7 @@ extern "C" {
 
 size_t gh_decode_workspace_bytes(uint64_t payload_bytes) { return gh::dec_layout(payload_bytes).total; }
 
-void gh_debug_select_writer(int warp_cooperative) { gh::g_writer = warp_cooperative ? 1 : 0; }
+void gh_debug_select_writer(int pipeline) { gh::g_pipeline = pipeline < 0 || pipeline > 2 ? 0 : pipeline; }
 
 int gh_decode_sync(const uint8_t* d_payload, uint64_t slice_bytes, uint64_t readable_bytes, const gh_code* code,
                    uint32_t entry_bit, int first_call, gh_shard_sync* result, void* d_workspace,
@@ -1217,7 +1321,7 @@ int gh_decode_write(const uint8_t* d_payload, uint64_t slice_bytes, uint64_t rea
   g.n_sub = h_ctl.n_sub;
   g.entry0 = 0;
   if (g.sub_bytes < kMinSubBytes || g.n_sub != (slice_bytes + g.sub_bytes - 1) / g.sub_bytes) return GH_ERR_ARG;
-  return decode_write_impl(g, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+  return decode_write_impl(g, h_ctl.fine != 0, d_out, out_cap, d_workspace, (cudaStream_t)stream);
 }
 
 int gh_decode(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code* code, uint8_t* d_out,
@@ -1234,12 +1338,13 @@ int decode_full(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code*
                 void* stream) {
   gh_shard_sync res;
   DecGeometry g;
+  bool fine = false;
   int rc = decode_sync_impl(d_payload, payload_bytes, payload_bytes, code, entry_bit, 1, &res, d_workspace,
-                            workspace_bytes, (cudaStream_t)stream, &g);
+                            workspace_bytes, (cudaStream_t)stream, &g, &fine);
   if (rc != GH_OK) return rc;
   if (n_out) *n_out = res.n_symbols;
   if (!d_out && out_cap) return GH_ERR_ARG;
-  rc = decode_write_impl(g, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+  rc = decode_write_impl(g, fine, d_out, out_cap, d_workspace, (cudaStream_t)stream);
   if (rc != GH_OK) return rc;
   GH_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   if (!res.eof_found) return GH_ERR_NO_EOF;

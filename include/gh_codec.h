@@ -66,9 +66,10 @@ uint64_t gh_launch_count(void);
  * (and resets the counters). Returns the bytes written. Off by default. */
 void gh_profile_enable(int on);
 size_t gh_profile_fetch(char* buf, size_t cap);
-/* Diagnostics only: pick the experimental warp-cooperative K7 writer (non-zero) or the default
- * thread-per-subsequence one (0) for A/B measurements. Output is identical either way. */
-void gh_debug_select_writer(int warp_cooperative);
+/* Diagnostics only: decode pipeline for A/B measurements -- 0 automatic (fine-grained warp-per-segment pipeline for
+ * codes that re-synchronise quickly, coarse thread-per-subsequence one otherwise), 1 always coarse, 2 always fine.
+ * Output is identical either way. */
+void gh_debug_select_writer(int pipeline);
 
 /* ------------------------------------------------------------------------------------------------
  * Host: code construction and the file header (microseconds; stays on the host by design)

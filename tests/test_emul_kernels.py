@@ -226,16 +226,19 @@ def test_emulated_histogram_pipelined_path(emu, oracle):
     assert (hist == oracle.histogram(raw[:n].tobytes())).all()
 
 
-def test_emulated_warp_cooperative_writer(emu, ctx, oracle):
-    """the experimental warp-per-subsequence K7 (shared-memory staging, warp-level self-sync) produces the same
-    bytes as the default writer"""
+@pytest.mark.parametrize("pipeline", [1, 2])
+def test_emulated_forced_pipelines(emu, ctx, oracle, pipeline):
+    """both decode pipelines forced in turn (1 = coarse thread-per-subsequence, 2 = fine warp-per-segment with stored
+    piece states) give the oracle's bytes on every kind of code, including the ones the automatic choice would
+    route the other way"""
     import golden_huffman_b200.workloads as W
-    emu.lib.gh_debug_select_writer(1)
+    emu.lib.gh_debug_select_writer(pipeline)
     try:
         rng = np.random.default_rng(8)
         cases = [make_input("text_small") * 30, W.zipf_np(70001, seed=2).tobytes(),
                  np.where(rng.random(90000) < 0.97, 7, rng.integers(0, 40, 90000)).astype(np.uint8).tobytes(),
-                 W.uniform_np(50000, seed=4).tobytes(), b"Z", make_input("kat1_abracadabra")]
+                 W.uniform_np(50000, seed=4).tobytes(), b"Z", make_input("kat1_abracadabra"),
+                 make_input("fib24_shuffled")]
         for data in cases:
             _roundtrip(emu, ctx, oracle, data)
     finally:

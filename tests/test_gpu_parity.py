@@ -300,3 +300,24 @@ def test_full_size_1gib(codec, oracle, workload):
     rc, oimg = oracle.compress(host)
     assert rc == 0 and len(oimg) == img.numel()
     assert hashlib.sha256(oimg).digest() == hashlib.sha256(img.cpu().numpy().tobytes()).digest()
+
+
+@pytest.mark.parametrize("pipeline", [1, 2])
+def test_forced_decode_pipelines(codec, oracle, pipeline):
+    """coarse (1) and fine (2) decode pipelines forced in turn: identical output on fast- and slow-synchronising codes"""
+    import torch
+    import golden_huffman_b200.workloads as w
+    codec.lib.lib.gh_debug_select_writer(pipeline)
+    try:
+        for name in ("zipf", "uniform", "skewed", "text"):
+            n = (1 << 23) + 77
+            x = w.WORKLOADS_TORCH[name](n, "cuda", seed=3)
+            img = codec.compress(x)
+            out, nd, rc = codec.decompress(img, n + 5)
+            assert rc == 0 and nd == n and torch.equal(out, x), (pipeline, name)
+        data = make_input("fib24_shuffled")
+        x = _cuda(np.frombuffer(data, dtype=np.uint8))
+        out, nd, rc = codec.decompress(codec.compress(x), len(data))
+        assert rc == 0 and nd == len(data) and _bytes(out) == data
+    finally:
+        codec.lib.lib.gh_debug_select_writer(0)

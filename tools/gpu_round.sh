@@ -33,7 +33,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "ncu launches exit $?"
   echo "== ncu full"
   [ "${SKIP_NCU_FULL:-0}" != "1" ] && $CMD > $OUT/${TAG}_ncu_plain2.log 2>&1 &&
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"hist_kernel|encode_kernel|dec_speculate_kernel|dec_sync_kernel|dec_write_kernel" -s ${NCU_SKIP:-24} -c ${NCU_COUNT:-8} -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"hist_kernel|encode_kernel|dec_.*speculate_kernel|dec_sync_kernel|dec_.*write_kernel" -s ${NCU_SKIP:-24} -c ${NCU_COUNT:-8} -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
   echo "ncu full exit $?"
 fi
 ls -la $OUT | tail -20

@@ -1058,8 +1058,8 @@ dec_fine_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, Dec
 }
 
 // ---- host orchestration -------------------------------------------------------------------------------
-// Pipeline choice: 0 = automatic (fine-grained for codes that re-synchronise quickly, coarse otherwise),
-// 1 = always coarse (one thread per subsequence), 2 = always fine. gh_debug_select_writer / GH_DECODE_PIPELINE
+// Pipeline choice: 0 = automatic (currently always the coarse one), 1 = always coarse (one thread per
+// subsequence), 2 = always fine (one warp per 2 KiB segment). gh_debug_select_writer / GH_DECODE_PIPELINE
 // ("coarse" / "fine") override the automatic choice for A/B runs; the output is identical either way.
 static int g_pipeline = -1;
 static int pipeline_choice() {
@@ -1175,7 +1175,8 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     GH_LAUNCH(dec_build_luts_kernel, (1u << kLutCBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
               const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW), const_cast<u32*>(ws.lutP));
     const bool slow_code = code->max_len - code->min_len <= 1;
-    fine = pipeline_choice() == 2 || (pipeline_choice() == 0 && !slow_code);
+    // measured (profiles/r1i): the fine pipeline is not yet faster than the coarse one, so it is opt-in
+    fine = pipeline_choice() == 2;
     g.sub_bytes = choose_sub_bytes(slice_bytes);
     // near-fixed-length codes (all lengths within one bit: uniform-looking bytes) re-synchronise only when one of
     // the rare longer codewords shifts the phase; start them 4x coarser (measured on uniform bytes: the paths need

@@ -66,8 +66,8 @@ uint64_t gh_launch_count(void);
  * (and resets the counters). Returns the bytes written. Off by default. */
 void gh_profile_enable(int on);
 size_t gh_profile_fetch(char* buf, size_t cap);
-/* Diagnostics only: decode pipeline for A/B measurements -- 0 automatic (fine-grained warp-per-segment pipeline for
- * codes that re-synchronise quickly, coarse thread-per-subsequence one otherwise), 1 always coarse, 2 always fine.
+/* Diagnostics only: decode pipeline for A/B measurements -- 0 automatic (currently the coarse
+ * thread-per-subsequence pipeline), 1 always coarse, 2 always fine (warp per 2 KiB segment, stored piece states).
  * Output is identical either way. */
 void gh_debug_select_writer(int pipeline);
 

@@ -301,12 +301,19 @@ def main():
             avg = ms / cnt
             kernels[name] = {"launches_per_step": cnt / prof_steps, "avg_ms": avg, "ms_per_step": ms / prof_steps,
                              "GBps": (alg_bytes(name) / (avg * 1e-3) / 1e9) if avg > 0 else None}
+        traffic_by_kernel = {}
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this same command
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if args.workload == "zipf" and args.size_mib == 1024:
+                traffic_by_kernel = tj.get("bytes_per_launch", {})
+        except Exception:
+            pass
         if prof:
             dom = max(prof, key=lambda k: prof[k][1])
             avg = prof[dom][1] / prof[dom][0]
             ach = alg_bytes(dom) / (avg * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                        "frac": ach / peak_gbs, "traffic": None, "peak_source": peak_src,
+                        "frac": ach / peak_gbs, "traffic": traffic_by_kernel.get(dom), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg_bytes(dom), "avg_launch_ms": avg}
     stage_roofline = {
         "encode": {"algorithmic_bytes": 2 * n_total + comp_total, "GBps": (2 * n_total + comp_total) * args.steps / (enc_ms * 1e-3) / 1e9},

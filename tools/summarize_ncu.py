@@ -55,12 +55,20 @@ if os.path.exists(rep):
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
     out.append("## ncu --set full (per launch; traffic = dram read + write)\n")
     seen = defaultdict(int)
+    traffic = {}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0]
         seen[name] += 1
         if seen[name] > 1:
             continue
         out.append(f"### {name}\n")
+        try:
+            unit_scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * unit_scale[units[idx["dram__bytes_read.sum"]]]
+            wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * unit_scale[units[idx["dram__bytes_write.sum"]]]
+            traffic[name.replace("void ", "")] = int(rd + wr)
+        except Exception:
+            pass
         for w in want:
             if w in idx:
                 out.append(f"- {w}: {r[idx[w]]} {units[idx[w]]}")
@@ -76,4 +84,9 @@ if os.path.exists(rep):
                    ", ".join(f"{h.split('issue_stalled_')[1].replace('.ratio', '')}={v:.2f}" for v, h in stalls[:6]))
         out.append("")
 open(os.path.join(dst, f"{tag}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+if rep and os.path.exists(rep):
+    import json
+    json.dump({"source": f"{tag}_prof.ncu-rep (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+               "workload": "1 GiB Zipf(1.1), 1 GPU (bench.py default)", "bytes_per_launch": traffic},
+              open(os.path.join(dst, f"traffic_{tag}.json"), "w"), indent=1)
 print("\n".join(out))

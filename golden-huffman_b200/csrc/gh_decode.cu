@@ -295,87 +295,65 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   u32 pos = entry, count = 0, neof = 0, first_eof = kNoEof;
   const bool bulk = end >= u32(kLutCBits);
   const u32 last = end - u32(kLutCBits);  // multi-codeword steps are allowed while pos <= last (only used if bulk)
-  // (a) bulk: two 15-bit lookups per iteration, one refill check for both (a hit consumes at most 15 bits, so the
-  //     second lookup still sees >= 17 valid bits; a miss -- long codeword or end mark -- refills first).
-  //     Per-lane "rare" events happen on almost every iteration of a 32-lane warp, so the loop is built to make
-  //     them few. Nothing taken from the table can cross `end`: both lookups start at pos <= end - 30.
-  if (bulk && end >= 2u * kLutCBits) {
-    const u32 last2 = end - 2u * kLutCBits;
+  // (a) bulk, word-synchronous (a two-lookups-per-iteration loop like K7's measured slower here: r1k): every lane pushes exactly one 32-bit word per step (statically indexed register of
+  //     the current 128-bit vector, next vector already requested), then takes table lookups while it holds >= 32
+  //     bits. The refill is unconditional straight-line code, so the only data-dependent control flow left in the
+  //     warp is the lookup loop itself. Nothing taken from the 15-bit table can cross `end`.
+  {
     const u64 bit0 = start + pos;
-    const u64 v0 = bit0 >> 7;
+    u64 v = bit0 >> 7;
+    u32 k0 = u32(bit0 >> 5) & 3u;  // words of the first vector that lie before the start (subsequence 0 only)
+    u32 drop = u32(bit0) & 31u;
     const u64 full_vecs = g.readable >> 4;
-    if (pos <= last2 && v0 + 2 < full_vecs) {
-      const uint4* vp = reinterpret_cast<const uint4*>(g.payload) + v0;  // vector indices below are relative to v0
-      uint4 cur = ldg128(vp), ahead = ldg128(vp + 1);
-      u32 vnext = 2;
-      const u64 span = full_vecs - v0;
-      const u32 vend = span > 0x7fffffffull ? 0x7fffffffu : u32(span);
-      u32 w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
-      const u32 skip = u32(bit0 >> 5) & 3u;
-      for (u32 k = 0; k < skip; ++k) w0 = w1, w1 = w2, w2 = w3;
-      u32 left = 4 - skip;
+    if (bulk && v + 1 < full_vecs) {
+      const uint4* vp = reinterpret_cast<const uint4*>(g.payload);
+      uint4 cur = ldg128(vp + v), nxt = ldg128(vp + v + 1);
       u64 buf = 0;
       int avail = 0;
-      auto push = [&]() {
-        buf |= u64(be32(w0)) << (32 - avail);
-        avail += 32;
-        w0 = w1, w1 = w2, w2 = w3;
-        if (--left == 0) {
-          w0 = ahead.x, w1 = ahead.y, w2 = ahead.z, w3 = ahead.w;
-          left = 4;
-          ahead = ldg128(vp + vnext);  // vnext < vend is the loop condition
-          ++vnext;
+      bool more = true;
+      while (more) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (u32(k) < k0) continue;
+          const u32 w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
+          buf |= u64(be32(w)) << (32 - avail);
+          avail += 32;
+          if (drop) buf <<= drop, avail -= int(drop), drop = 0;
+          while (avail >= 32 && pos <= last) {
+            const u32 win = u32(buf >> 32);
+            const u32 e = s.lutC[win >> (32 - kLutCBits)];
+            u32 len;
+            if (e) {
+              len = e & 15u;
+              count += e >> 4;
+            } else {  // first codeword longer than 15 bits, or the end mark
+              u32 sym;
+              decode_one(s.canon, s.lut1, win, sym, len);
+              if (sym == u32(GH_EOF_SYMBOL)) {
+                if (!neof) first_eof = count;
+                ++neof;
+              }
+              ++count;
+            }
+            pos += len;
+            buf <<= len;
+            avail -= int(len);
+          }
+          if (pos > last) {
+            more = false;
+            break;
+          }
         }
-      };
-      push();
-      push();
-      {
-        const u32 drop = u32(bit0) & 31u;
-        buf <<= drop;
-        avail -= int(drop);
-        if (avail < 32) push();
-      }
-      auto miss = [&](u32 win, u32& len) {  // codeword longer than 15 bits, or the end mark
-        u32 sym;
-        decode_one(s.canon, s.lut1, win, sym, len);
-        if (sym == u32(GH_EOF_SYMBOL)) {
-          if (!neof) first_eof = count;
-          ++neof;
-        }
-        ++count;
-      };
-      while (pos <= last2 && vnext < vend) {
-        u32 win = u32(buf >> 32);
-        u32 e = s.lutC[win >> (32 - kLutCBits)];
-        u32 len;
-        if (e) {
-          len = e & 15u;
-          count += e >> 4;
-        } else {
-          miss(win, len);
-        }
-        pos += len;
-        buf <<= len;
-        avail -= int(len);
-        if (avail < int(kLutCBits)) push();  // only after a long codeword
-        win = u32(buf >> 32);
-        e = s.lutC[win >> (32 - kLutCBits)];
-        if (e) {
-          len = e & 15u;
-          count += e >> 4;
-        } else {
-          if (avail < 32) push();
-          win = u32(buf >> 32);
-          miss(win, len);
-        }
-        pos += len;
-        buf <<= len;
-        avail -= int(len);
-        if (avail < 32) push();
+        k0 = 0;
+        if (!more) break;
+        ++v;
+        if (v + 1 >= full_vecs) break;  // the last vectors of the payload go through the bounds-checked reader
+        cur = nxt;
+        nxt = ldg128(vp + v + 1);
       }
     }
   }
-  // (a') whatever the bulk loop left (last 30 bits, payload tail): single lookups through the bounds-checked reader
+  // (a') whatever the bulk loop left (payload tail), same steps through the bounds-checked reader
   BitReader r;
   r.seek(g.payload, g.readable, start + pos);
   while (bulk && pos <= last) {

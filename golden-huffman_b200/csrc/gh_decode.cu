@@ -305,9 +305,9 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
     u32 k0 = u32(bit0 >> 5) & 3u;  // words of the first vector that lie before the start (subsequence 0 only)
     u32 drop = u32(bit0) & 31u;
     const u64 full_vecs = g.readable >> 4;
-    if (bulk && v + 1 < full_vecs) {
+    if (bulk && v + 2 < full_vecs) {
       const uint4* vp = reinterpret_cast<const uint4*>(g.payload);
-      uint4 cur = ldg128(vp + v), nxt = ldg128(vp + v + 1);
+      uint4 cur = ldg128(vp + v), nxt = ldg128(vp + v + 1), nxt2 = ldg128(vp + v + 2);  // two vectors in flight
       u64 buf = 0;
       int avail = 0;
       bool more = true;
@@ -347,9 +347,10 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
         k0 = 0;
         if (!more) break;
         ++v;
-        if (v + 1 >= full_vecs) break;  // the last vectors of the payload go through the bounds-checked reader
+        if (v + 2 >= full_vecs) break;  // the last vectors of the payload go through the bounds-checked reader
         cur = nxt;
-        nxt = ldg128(vp + v + 1);
+        nxt = nxt2;
+        nxt2 = ldg128(vp + v + 2);
       }
     }
   }
@@ -703,10 +704,12 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
     const u64 bit0 = start + pos;
     const u64 v0 = bit0 >> 7;
     const u64 full_vecs = g.readable >> 4;
-    if (remaining >= u32(kLutWMaxSyms) && v0 + 2 < full_vecs) {
+    if (remaining >= u32(kLutWMaxSyms) && v0 + 3 < full_vecs) {
       const uint4* vp = reinterpret_cast<const uint4*>(g.payload) + v0;  // vector indices below are relative to v0
-      uint4 cur = ldg128(vp), ahead = ldg128(vp + 1);
-      u32 vnext = 2;  // next vector to request
+      // two vectors are kept in flight ahead of the one being consumed: with ~half of the warp slots of an SM
+      // occupied, one was not enough to cover the load latency (long-scoreboard stalls on top in profiles/r1j)
+      uint4 cur = ldg128(vp), ahead = ldg128(vp + 1), ahead2 = ldg128(vp + 2);
+      u32 vnext = 3;  // next vector to request
       const u64 span = full_vecs - v0;
       const u32 vend = span > 0x7fffffffull ? 0x7fffffffu : u32(span);  // vectors that may be requested
       u32 w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
@@ -722,7 +725,8 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         if (--left == 0) {
           w0 = ahead.x, w1 = ahead.y, w2 = ahead.z, w3 = ahead.w;
           left = 4;
-          ahead = ldg128(vp + vnext);  // vnext < vend is the loop condition
+          ahead = ahead2;
+          ahead2 = ldg128(vp + vnext);  // vnext < vend is the loop condition
           ++vnext;
         }
       };

@@ -47,6 +47,18 @@ __device__ __forceinline__ u32 be32(u32 little_endian_word) { return __byte_perm
 // 128-bit read-only load (LDG.E.128.CONSTANT)
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
 
+// Same load, but pinned to `dst`'s registers: as an opaque asm statement it cannot be merged with a sibling load
+// on another path and copied over afterwards (a copy that waits for the load and defeats a software prefetch).
+__device__ __forceinline__ void ldg128_into(uint4& dst, const uint4* p) {
+#ifdef GH_EMUL
+  dst = *p;
+#else
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(dst.x), "=r"(dst.y), "=r"(dst.z), "=r"(dst.w)
+               : "l"(p));
+#endif
+}
+
 // Single-word flag|value messages between thread blocks: relaxed, GPU scope (served by L2, no system-scope
 // round trip). One 64-bit word carries flag and value together, so no fence is needed around them.
 __device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
@@ -63,6 +75,27 @@ __device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
   __atomic_store_n(p, v, __ATOMIC_SEQ_CST);
 #else
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+
+// Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS): the data never passes through registers, so a
+// software prefetch cannot be undone by register copies that wait for the load.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef GH_EMUL
+  memcpy(smem_dst, gsrc, 16);
+#else
+  const unsigned s = unsigned(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef GH_EMUL
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all_but_one() {  // the older of two groups in flight has landed
+#ifndef GH_EMUL
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
 #endif
 }
 

@@ -629,13 +629,11 @@ struct SmemWrite {
   uint16_t lut1[1 << kLut1Bits];
   u32 lutW[1 << kLutWBits];
   u32 warp_total[kDecThreads / 32];
-  __align__(16) uint4 ring[3 * kDecThreads];  // per-lane prefetch ring (cp.async)
 };
 
 __global__ void __launch_bounds__(kDecThreads)
 dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
-  GH_DYNAMIC_SMEM(smem_raw);
-  SmemWrite& s = *reinterpret_cast<SmemWrite*>(smem_raw);
+  __shared__ SmemWrite s;
   load_canon(s.canon, ws.tables);
   for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
     reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
@@ -706,21 +704,10 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
     const u64 bit0 = start + pos;
     const u64 v0 = bit0 >> 7;
     const u64 full_vecs = g.readable >> 4;
-    if (remaining >= u32(kLutWMaxSyms) && v0 + 3 < full_vecs) {
+    if (remaining >= u32(kLutWMaxSyms) && v0 + 2 < full_vecs) {
       const uint4* vp = reinterpret_cast<const uint4*>(g.payload) + v0;  // vector indices below are relative to v0
-      // Two vectors are kept in flight ahead of the one being consumed, through a per-lane ring of three 16-byte
-      // slots in shared memory filled by cp.async (LDGSTS): the prefetched data never sits in registers. (As plain
-      // register prefetch, `ahead = ldg(...)`, ptxas loaded into scratch registers and copied them over right
-      // away -- a move that waits for the load: 46 % of all stall samples of this kernel in profiles/r1j; neither
-      // named ping-pong registers nor asm-pinned loads survived its if-conversion.)
-      uint4* ring = s.ring + threadIdx.x;  // slot k of this lane: ring[k * kDecThreads]
-      const uint4 cur = ldg128(vp);
-      cp_async16(ring, vp + 1);
-      cp_async_commit();
-      cp_async16(ring + kDecThreads, vp + 2);
-      cp_async_commit();
-      u32 slot = 0;   // slot holding the next vector to consume
-      u32 vnext = 3;  // next vector to request
+      uint4 cur = ldg128(vp), ahead = ldg128(vp + 1);
+      u32 vnext = 2;  // next vector to request
       const u64 span = full_vecs - v0;
       const u32 vend = span > 0x7fffffffull ? 0x7fffffffu : u32(span);  // vectors that may be requested
       u32 w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
@@ -734,15 +721,9 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         avail += 32;
         w0 = w1, w1 = w2, w2 = w3;
         if (--left == 0) {
+          w0 = ahead.x, w1 = ahead.y, w2 = ahead.z, w3 = ahead.w;
           left = 4;
-          cp_async_wait_all_but_one();
-          const uint4 v = ring[slot * kDecThreads];
-          w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
-          // refill the slot consumed one reload ago (two slots hold data in flight, the third is free)
-          const u32 free_slot = slot >= 1 ? slot - 1 : 2;
-          cp_async16(ring + free_slot * kDecThreads, vp + vnext);  // vnext < vend is the loop condition
-          cp_async_commit();
-          slot = slot == 2 ? 0 : slot + 1;
+          ahead = ldg128(vp + vnext);  // vnext < vend is the loop condition
           ++vnext;
         }
       };
@@ -1097,8 +1078,6 @@ static int set_fine_attrs() {  // opt-in to > 48 KB of dynamic shared memory for
                                      int(sizeof(SmemFineSpec))));
     GH_CUDA_TRY(cudaFuncSetAttribute(dec_fine_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      int(sizeof(SmemFineWrite))));
-    GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     int(sizeof(SmemWrite))));
     done = true;
   }
   return GH_OK;
@@ -1303,10 +1282,8 @@ static int decode_write_impl(const DecGeometry& g, bool fine, uint8_t* d_out, u6
     const unsigned blocks = unsigned((g.n_sub + kFineWarps - 1) / kFineWarps);
     GH_LAUNCH(dec_fine_write_kernel, blocks, kFineWarps * 32, sizeof(SmemFineWrite), stream, g, d_out, out_cap, ws);
   } else {
-    int rc = set_fine_attrs();  // also raises dec_write_kernel's dynamic shared memory limit
-    if (rc != GH_OK) return rc;
     const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
-    GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, sizeof(SmemWrite), stream, g, d_out, out_cap, ws);
+    GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, 0, stream, g, d_out, out_cap, ws);
   }
   return check_launch();
 }

@@ -194,7 +194,7 @@ def main():
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
-    lib = gh.GhLib()
+    lib = gh.GhLib(os.environ.get("GH_LIB_PATH") or None)  # GH_LIB_PATH: a tuning build (build.py build_variant)
     codec = gh.Codec(lib)
     stream = torch.cuda.current_stream()
     lib.ctx_set_stream(codec.ctx, stream.cuda_stream)

@@ -34,6 +34,18 @@ def _newer(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+def build_variant(name, defines):
+    """tuning builds: lib/libgh_b200_<name>.so with -D overrides of the kernels' compile-time parameters
+    (select with GH_LIB_PATH in bench.py); not used by the product or the tests"""
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = [os.path.join(CSRC, f) for f in CU_SOURCES + CC_SOURCES]
+    out = os.path.join(LIBDIR, f"libgh_b200_{name}.so")
+    cmd = [_nvcc(), "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"),
+           "-I" + CSRC, "-shared", "-cudart", "static", *["-D" + d for d in defines], "-o", out, *srcs]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in CU_SOURCES + CC_SOURCES]

@@ -34,6 +34,12 @@
 namespace gh {
 
 constexpr int kDecThreads = 256;   // threads per block = subsequences per tile, all decode kernels
+#ifndef GH_DEC_S_BLOCKS
+#define GH_DEC_S_BLOCKS 6
+#endif
+#ifndef GH_DEC_W_BLOCKS
+#define GH_DEC_W_BLOCKS 1
+#endif
 constexpr u32 kNoEof = 0xffffffffu;
 constexpr u32 kEofPosUnknown = 0xfffffffeu;
 constexpr u32 kMinSubBytes = 128;
@@ -70,7 +76,7 @@ struct DecControl {  // device-resident, copied back to the host after each roun
 struct DecWorkspace {
   const DecodeTables* tables;  // small canonical tables (host-built)
   const uint16_t* lut1;        // [2^12]  device-built, see gh_internal.h
-  const uint8_t* lutC;         // [2^15]
+  const uint8_t* lutC;         // [2^14]
   const u32* lutW;             // [2^13]
   const u32* lutP;             // [2^12]
   DecControl* ctl;
@@ -261,14 +267,14 @@ __device__ __forceinline__ u64 sub_end_bits(const DecGeometry& g, u64 i) {
 }
 
 // ---- K5a: speculative decode of every subsequence from bit 0 (subsequence 0: from the true entry) ---------
-// Only counts are needed here, so the walk takes as many whole codewords per lookup as fit in 15 bits.
+// Only counts are needed here, so the walk takes as many whole codewords per lookup as fit in 14 bits (kLutCBits).
 struct SmemSpeculate {
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
   uint8_t lutC[1 << kLutCBits];
 };
 
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, GH_DEC_S_BLOCKS)
 dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   __shared__ SmemSpeculate s;
   load_canon(s.canon, ws.tables);
@@ -298,7 +304,7 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   // (a) bulk, word-synchronous (a two-lookups-per-iteration loop like K7's measured slower here: r1k): every lane pushes exactly one 32-bit word per step (statically indexed register of
   //     the current 128-bit vector, next vector already requested), then takes table lookups while it holds >= 32
   //     bits. The refill is unconditional straight-line code, so the only data-dependent control flow left in the
-  //     warp is the lookup loop itself. Nothing taken from the 15-bit table can cross `end`.
+  //     warp is the lookup loop itself. Nothing taken from the kLutCBits-bit table can cross `end`.
   {
     const u64 bit0 = start + pos;
     u64 v = bit0 >> 7;
@@ -326,7 +332,7 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
             if (e) {
               len = e & 15u;
               count += e >> 4;
-            } else {  // first codeword longer than 15 bits, or the end mark
+            } else {  // first codeword longer than the table window, or the end mark
               u32 sym;
               decode_one(s.canon, s.lut1, win, sym, len);
               if (sym == u32(GH_EOF_SYMBOL)) {
@@ -429,7 +435,7 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
     BitReader ra, rb;
     ra.seek(g.payload, g.readable, start + pos_a);
     rb.seek(g.payload, g.readable, start + pos_b);
-    // Both paths take the same kind of step from a given position (as many whole codewords as fit in 15 bits
+    // Both paths take the same kind of step from a given position (as many whole codewords as fit in kLutCBits bits
     // while that window lies inside the subsequence, else one codeword), so equal positions mean equal futures.
     // A boundary that one path steps over can be a stepping point of the other: they then meet a little later,
     // or not at all inside the subsequence -- in which case B has simply been walked to its end, which is exact.
@@ -520,7 +526,7 @@ dec_tile_sum_kernel(DecGeometry g, DecWorkspace ws) {
 // The first subsequence (in stream order) whose synchronised path contains an end mark ends the stream. The number
 // of symbols before that mark is normally already known (eofpos, kept by the walks above); when the mark lay in a
 // reused tail whose own first end mark was a false one, that one subsequence is walked again by a single thread
-// (tables staged in shared memory by the whole block, 15-bit multi-codeword steps).
+// (tables staged in shared memory by the whole block, multi-codeword steps).
 __global__ void __launch_bounds__(kDecThreads)
 dec_locate_eof_kernel(DecGeometry g, DecWorkspace ws) {
   __shared__ SmemSpeculate s;
@@ -631,7 +637,7 @@ struct SmemWrite {
   u32 warp_total[kDecThreads / 32];
 };
 
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, GH_DEC_W_BLOCKS)
 dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
   __shared__ SmemWrite s;
   load_canon(s.canon, ws.tables);

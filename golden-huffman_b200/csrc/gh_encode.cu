@@ -30,11 +30,17 @@ namespace gh {
 constexpr int kEncThreads = 256;
 constexpr int kEncBytesPerThread = 16;
 constexpr int kEncSubTileBytes = kEncThreads * kEncBytesPerThread;  // 4 KiB
-constexpr int kEncSubTiles = 4;
+#ifndef GH_ENC_SUBTILES
+#define GH_ENC_SUBTILES 4
+#endif
+#ifndef GH_ENC_BLOCKS_PER_SM
+#define GH_ENC_BLOCKS_PER_SM 5
+#endif
+constexpr int kEncSubTiles = GH_ENC_SUBTILES;
 constexpr int kEncTileBytes = kEncSubTileBytes * kEncSubTiles;      // 16 KiB per look-back
 // worst case per sub-tile: 4096 symbols x 32 bits + end mark 32, plus slack for the funnel shift
 constexpr int kEncStageWords = (kEncSubTileBytes * 32 + 32 + 31) / 32 + 2;
-constexpr int kEncBlocksPerSm = 4;
+constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
 
 constexpr u64 kFlagMask = 3ull << 62;
 constexpr u64 kFlagAggregate = 1ull << 62;  // value = bits of this tile only
@@ -75,7 +81,7 @@ __device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
 }
 
 template <int kSymsPerChunk>
-__global__ void __launch_bounds__(kEncThreads)
+__global__ void __launch_bounds__(kEncThreads, kEncBlocksPerSm)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
               u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
   constexpr int kChunks = kEncBytesPerThread / kSymsPerChunk;

@@ -15,7 +15,7 @@ namespace gh {
 //   lut1  2^12 x u16   one codeword per lookup: (symbol << 6) | length, 0 = codeword longer than 12 bits.
 //                      The device analogue of TableCanonicalHuffDecoder::lookup_table_
 //                      (reference include/canonical_huff_encoder.cc:466-516) with the symbol folded in.
-//   lutC  2^15 x u8    as many whole codewords as fit in 15 bits (never the end mark): (count << 4) | total length,
+//   lutC  2^14 x u8    as many whole codewords as fit in 14 bits (never the end mark): (count << 4) | total length,
 //                      0 = the first codeword does not fit or is the end mark. Used where only counts matter.
 //   lutW  2^13 x u32   up to 3 whole codewords in 13 bits: total length | count << 4 | symbols << 8 (first symbol
 //                      in the lowest byte), 0 = first codeword does not fit or is the end mark.
@@ -24,8 +24,14 @@ namespace gh {
 //                      0 = first codeword does not fit or is the end mark. Used by the warp-cooperative writer.
 constexpr int kLut1Bits = 12;
 constexpr int kLutPBits = 12;
-constexpr int kLutCBits = 15;
-constexpr int kLutWBits = 13;
+#ifndef GH_LUTC_BITS
+#define GH_LUTC_BITS 14
+#endif
+#ifndef GH_LUTW_BITS
+#define GH_LUTW_BITS 13
+#endif
+constexpr int kLutCBits = GH_LUTC_BITS;
+constexpr int kLutWBits = GH_LUTW_BITS;
 constexpr int kLutWMaxSyms = 3;
 
 struct DecodeTables {

@@ -107,8 +107,9 @@ int gh_compress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_ou
   size_t written = 0;
   rc = gh_write_header(&code, h_hdr, kMaxHeader, &written);
   if (rc != GH_OK) return rc;
-  // 3. payload (encode_file): the header is 8-byte aligned, the packer wants 16 -> start 64 bits into the vector
-  const size_t base = hdr & ~size_t(15);
+  // 3. payload (encode_file): the header is 8-byte aligned, the kernels work from the 32-byte boundary below it ->
+  //    the packer starts up to 192 bits into that sector
+  const size_t base = hdr & ~size_t(31);
   const uint64_t start_bit = uint64_t(hdr - base) * 8;
   rc = grow(&c->d_ws, &c->ws_cap, gh_encode_workspace_bytes(n));
   if (rc != GH_OK) return rc;
@@ -135,8 +136,8 @@ int gh_decompress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_
   int rc = gh_parse_header(h_hdr, peek, &code, &hdr);
   if (rc != GH_OK) return rc;
   if (n <= hdr) return GH_ERR_NO_EOF;
-  // 2. payload (decode_file)
-  const size_t base = hdr & ~size_t(15);
+  // 2. payload (decode_file), read from the 32-byte boundary below it (one sector per lane and request)
+  const size_t base = hdr & ~size_t(31);
   const uint64_t slice = n - base;
   rc = grow(&c->d_ws, &c->ws_cap, gh_decode_workspace_bytes(slice));
   if (rc != GH_OK) return rc;

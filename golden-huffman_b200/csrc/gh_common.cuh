@@ -47,6 +47,36 @@ __device__ __forceinline__ u32 be32(u32 little_endian_word) { return __byte_perm
 // 128-bit read-only load (LDG.E.128.CONSTANT)
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
 
+// One 32-byte sector per lane in a single request (LDG.E.ENL2.256, new with sm_100): lanes that stream their own
+// subsequences touch one sector per request instead of half of one, which halves the L1 wavefronts of these
+// fully divergent loads. `p` must be 32-byte aligned for the 256-bit form; a base that is only 16-byte aligned
+// takes two 128-bit loads instead (block-uniform choice).
+struct Unit8 {
+  u32 w[8];
+};
+__device__ __forceinline__ Unit8 ldg_unit(const uint8_t* p, bool aligned32) {
+  Unit8 u;
+#ifdef GH_EMUL
+  (void)aligned32;
+  memcpy(u.w, p, 32);
+#else
+  if (aligned32) {
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(u.w[0]), "=r"(u.w[1]), "=r"(u.w[2]), "=r"(u.w[3]), "=r"(u.w[4]), "=r"(u.w[5]), "=r"(u.w[6]),
+                   "=r"(u.w[7])
+                 : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(u.w[0]), "=r"(u.w[1]), "=r"(u.w[2]), "=r"(u.w[3])
+                 : "l"(p));
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(u.w[4]), "=r"(u.w[5]), "=r"(u.w[6]), "=r"(u.w[7])
+                 : "l"(p + 16));
+  }
+#endif
+  return u;
+}
+
 // Same load, but pinned to `dst`'s registers: as an opaque asm statement it cannot be merged with a sibling load
 // on another path and copied over afterwards (a copy that waits for the load and defeats a software prefetch).
 __device__ __forceinline__ void ldg128_into(uint4& dst, const uint4* p) {
@@ -98,6 +128,37 @@ __device__ __forceinline__ void cp_async_wait_all_but_one() {  // the older of t
   asm volatile("cp.async.wait_group 1;" ::: "memory");
 #endif
 }
+
+// Shared-memory loads by 32-bit shared-window address (LDS [reg + imm]): a table lookup whose byte offset was
+// produced by a mask needs no further address arithmetic, and no generic-to-shared conversion is re-derived inside
+// the loop (which is what indexing through a generic pointer compiles to).
+#ifdef GH_EMUL
+typedef const char* smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void* p) { return static_cast<const char*>(p); }
+__device__ __forceinline__ u32 lds_u16(smem_addr_t base, u32 byte_off) {
+  return *reinterpret_cast<const uint16_t*>(base + byte_off);
+}
+__device__ __forceinline__ uint2 lds_v2(smem_addr_t base, u32 byte_off) {
+  return *reinterpret_cast<const uint2*>(base + byte_off);
+}
+#else
+typedef u32 smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void* p) {
+  u32 a = u32(__cvta_generic_to_shared(p));
+  asm volatile("" : "+r"(a));  // opaque: keeps the address in a register instead of re-deriving it at every use
+  return a;
+}
+__device__ __forceinline__ u32 lds_u16(smem_addr_t base, u32 byte_off) {
+  u32 v;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_v2(smem_addr_t base, u32 byte_off) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(base + byte_off));
+  return v;
+}
+#endif
 
 // inclusive warp scan (Kogge-Stone over shuffles)
 __device__ __forceinline__ u32 warp_inclusive_scan(u32 v, unsigned lane) {

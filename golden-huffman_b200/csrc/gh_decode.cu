@@ -35,7 +35,7 @@ namespace gh {
 
 constexpr int kDecThreads = 256;   // threads per block = subsequences per tile, all decode kernels
 #ifndef GH_DEC_S_BLOCKS
-#define GH_DEC_S_BLOCKS 6
+#define GH_DEC_S_BLOCKS 5
 #endif
 #ifndef GH_DEC_W_BLOCKS
 #define GH_DEC_W_BLOCKS 1
@@ -76,8 +76,8 @@ struct DecControl {  // device-resident, copied back to the host after each roun
 struct DecWorkspace {
   const DecodeTables* tables;  // small canonical tables (host-built)
   const uint16_t* lut1;        // [2^12]  device-built, see gh_internal.h
-  const uint8_t* lutC;         // [2^14]
-  const u32* lutW;             // [2^13]
+  const uint16_t* lutC;        // [2^kLutCBits]
+  const uint2* lutW;           // [2^kLutWBits]
   const u32* lutP;             // [2^12]
   DecControl* ctl;
   u64* sub;        // [n_sub]
@@ -140,8 +140,8 @@ __device__ __forceinline__ void decode_one(const SmemCanon& s, const uint16_t* l
 // ---- K5 prologue: expand the canonical tables into the lookup tables, on the device -------------------------
 // thread w handles window value w of each table it is in range for
 __global__ void __launch_bounds__(256)
-dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restrict__ lut1, uint8_t* __restrict__ lutC,
-                      u32* __restrict__ lutW, u32* __restrict__ lutP) {
+dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restrict__ lut1, uint16_t* __restrict__ lutC,
+                      uint2* __restrict__ lutW, u32* __restrict__ lutP) {
   __shared__ SmemCanon s;
   load_canon(s, tables);
   __syncthreads();
@@ -157,7 +157,7 @@ dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restr
       u32 sym, len;
       canon_search(s, win, min_len, sym, len);
       if (int(len) > avail || sym == u32(GH_EOF_SYMBOL)) break;
-      if (nsym < 3) packed |= (sym & 0xffu) << (8 * nsym);
+      if (nsym < 4) packed |= (sym & 0xffu) << (8 * nsym);
       ++nsym;
       total_len += len;
       win = len < 32 ? win << len : 0u;
@@ -166,12 +166,12 @@ dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restr
   };
   u32 tl, ns, pk;
   if (w < (1u << kLutCBits)) {
-    walk(w, kLutCBits, 15, tl, ns, pk);
-    lutC[w] = uint8_t(ns ? ((ns << 4) | tl) : 0u);
+    walk(w, kLutCBits, 64, tl, ns, pk);
+    lutC[w] = uint16_t(ns ? ((ns << kCurShift) - tl) : kLutMiss);
   }
   if (w < (1u << kLutWBits)) {
     walk(w, kLutWBits, kLutWMaxSyms, tl, ns, pk);
-    lutW[w] = ns ? (tl | (ns << 4) | (pk << 8)) : 0u;
+    lutW[w] = ns ? make_uint2((ns << (kCurShift + 3)) - tl, pk) : make_uint2(kLutMiss, 0u);
   }
   if (w < (1u << kLutPBits)) {
     walk(w, kLutPBits, 2, tl, ns, pk);
@@ -266,22 +266,93 @@ __device__ __forceinline__ u64 sub_end_bits(const DecGeometry& g, u64 i) {
   return left < full ? left : full;
 }
 
+// ---- cursor reader: the bulk loops of K5a and K7 -------------------------------------------------------------
+// A lane holds two consecutive big-endian stream words (hi:lo) and ONE cursor word `acc` whose low ten bits F say
+// where the next codeword starts:  F = 512 + s, where s = S0 - (bits of hi:lo already consumed) is exactly the
+// funnel-shift distance that brings the next K-bit window, pre-scaled by the table's entry size, to the bottom of
+// a register (SHF.R.W takes its distance modulo 32, so `acc` itself is the shift operand). A lookup is
+//     x = (hi:lo) >> acc;   e = table[x & mask];   acc += e;                        (SHF, LOP3, LDS, IADD)
+// because a table entry is stored as the addend  (what the kernel counts << 10) - (bits consumed).  Lookups are
+// allowed while s is in [0, 32), i.e. F in [512, 544), i.e. (acc & 0x1E0) == 0 -- one LOP3 -- and the loop around
+// them is word-synchronous: every lane takes the next word of its 32-byte unit (one LDG.256 per lane) from a
+// statically indexed register (F += 32), then looks up while allowed. F in [192, 512) means "window not inside
+// hi:lo yet": that is the state after a lookup crossed into the next word, and it is also how a lane starts in
+// the middle of a unit -- F starts up to nine words low and the first rotations are dummies, so the loop needs no
+// per-word bounds tests. F never leaves [192, 576), so nothing ever borrows from or carries into the bits above.
+// A table miss (first codeword longer than K bits, or the end mark) is the entry kLutMiss = 32: F lands in
+// [544, 576) (bit 9 and bit 5 set), the lookup loop ends, and the codeword is resolved with the canonical search
+// (reference include/canonical_huff_encoder.cc:437-453) on a 32-bit window built from hi, lo and the next word.
+constexpr u32 kCurBase = 512u;
+constexpr u32 kCurBusy = 0x1E0u;     // any of these bits set: no lookup now
+constexpr u32 kCurMissBit = 0x200u;  // ... and this one set as well: the last lookup missed
+constexpr u32 kCurFieldMask = 0x3ffu;
+constexpr int kUnitWords = 8;        // a lane's reads are 32-byte units
+
+template <int K, int SC>  // K index bits, entries of (1 << SC) bytes
+struct CursorGeom {
+  static constexpr int S0 = 64 - K - SC;  // shift distance of the last window position inside hi:lo
+  static constexpr int CMIN = S0 - 31;    // consumed bits of hi:lo at the first one
+  static constexpr u32 kMask = ((1u << K) - 1u) << SC;
+};
+
+// Plans the bulk part of a walk from absolute bit `bit0` that must not take a K-bit window beyond `end_abs`:
+// units u0..ulast are consumed whole; afterwards the position is cursor_position().
+template <int K, int SC>
+__device__ __forceinline__ bool cursor_plan(u64 bit0, u64 end_abs, u64 full_units, u64& u0, u64& ulast, u32& f0) {
+  typedef CursorGeom<K, SC> G;
+  if (end_abs < u64(K + G::S0) + 32 * kUnitWords || full_units < 2) return false;
+  const u64 jmax = (end_abs - u64(K + G::S0)) >> 5;  // last word that may be `hi` while lookups are taken
+  u64 ul = (jmax - (kUnitWords - 2)) / kUnitWords;   // its unit must be complete: word 8 * ul + 7 <= jmax + 1
+  if (ul > full_units - 2) ul = full_units - 2;      // and the unit after it readable (miss path, prefetch)
+  u0 = bit0 >> 8;
+  if (ul < u0) return false;
+  const int f = int(u32(bit0) & 255u);
+  const int jrel = (f - G::CMIN) >> 5;  // word of u0 that is `hi` at the first lookup (-1: the word before u0)
+  const int c = f - 32 * jrel;          // consumed bits of hi:lo at that point, CMIN .. CMIN + 31
+  f0 = u32(int(kCurBase) + G::S0 - c - 32 * (jrel + 2));
+  ulast = ul;
+  return true;
+}
+
+template <int K, int SC>
+__device__ __forceinline__ u64 cursor_position(u64 ulast, u32 acc) {
+  return 32ull * (u64(kUnitWords) * ulast + u64(kUnitWords - 2)) +
+         u64(CursorGeom<K, SC>::S0 + int(kCurBase) - int(acc & kCurFieldMask));
+}
+
+// the 32 stream bits at the cursor of a lane whose last lookup missed (F already reduced by kLutMiss)
+template <int K, int SC>
+__device__ __forceinline__ u32 cursor_window32(u32 hi, u32 lo, u32 next_raw, u32 acc) {
+  const u32 c = u32(CursorGeom<K, SC>::S0 + int(kCurBase) - int(acc & kCurFieldMask));  // CMIN .. S0
+  return c < 32u ? __funnelshift_l(lo, hi, c) : __funnelshift_l(be32(next_raw), lo, c - 32u);
+}
+
+__device__ __forceinline__ bool lutc_hit(u32 e, u32& len, u32& cnt) {  // for the walks outside the bulk loops
+  cnt = (e + ((1u << kCurShift) - 1u)) >> kCurShift;
+  len = (cnt << kCurShift) - e;
+  return e != kLutMiss;
+}
+
 // ---- K5a: speculative decode of every subsequence from bit 0 (subsequence 0: from the true entry) ---------
 // Only counts are needed here, so the walk takes as many whole codewords per lookup as fit in 14 bits (kLutCBits).
 struct SmemSpeculate {
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
-  uint8_t lutC[1 << kLutCBits];
+  uint16_t lutC[1 << kLutCBits];
 };
+
+__device__ __forceinline__ void load_speculate_tables(SmemSpeculate& s, const DecWorkspace& ws) {
+  load_canon(s.canon, ws.tables);
+  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 8; i += kDecThreads)
+    reinterpret_cast<uint4*>(s.lut1)[i] = reinterpret_cast<const uint4*>(ws.lut1)[i];
+  for (unsigned i = threadIdx.x; i < (1u << kLutCBits) / 8; i += kDecThreads)
+    reinterpret_cast<uint4*>(s.lutC)[i] = reinterpret_cast<const uint4*>(ws.lutC)[i];
+}
 
 __global__ void __launch_bounds__(kDecThreads, GH_DEC_S_BLOCKS)
 dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   __shared__ SmemSpeculate s;
-  load_canon(s.canon, ws.tables);
-  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
-    reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
-  for (unsigned i = threadIdx.x; i < (1u << kLutCBits) / 16; i += kDecThreads)
-    reinterpret_cast<uint4*>(s.lutC)[i] = reinterpret_cast<const uint4*>(ws.lutC)[i];
+  load_speculate_tables(s, ws);
   __syncthreads();
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
   if (i >= g.n_sub) return;
@@ -301,63 +372,50 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   u32 pos = entry, count = 0, neof = 0, first_eof = kNoEof;
   const bool bulk = end >= u32(kLutCBits);
   const u32 last = end - u32(kLutCBits);  // multi-codeword steps are allowed while pos <= last (only used if bulk)
-  // (a) bulk, word-synchronous (a two-lookups-per-iteration loop like K7's measured slower here: r1k): every lane pushes exactly one 32-bit word per step (statically indexed register of
-  //     the current 128-bit vector, next vector already requested), then takes table lookups while it holds >= 32
-  //     bits. The refill is unconditional straight-line code, so the only data-dependent control flow left in the
-  //     warp is the lookup loop itself. Nothing taken from the kLutCBits-bit table can cross `end`.
+  // (a) bulk: the cursor reader above. Nothing taken from the kLutCBits-bit table can cross `end`.
   {
-    const u64 bit0 = start + pos;
-    u64 v = bit0 >> 7;
-    u32 k0 = u32(bit0 >> 5) & 3u;  // words of the first vector that lie before the start (subsequence 0 only)
-    u32 drop = u32(bit0) & 31u;
-    const u64 full_vecs = g.readable >> 4;
-    if (bulk && v + 2 < full_vecs) {
-      const uint4* vp = reinterpret_cast<const uint4*>(g.payload);
-      uint4 cur = ldg128(vp + v), nxt = ldg128(vp + v + 1), nxt2 = ldg128(vp + v + 2);  // two vectors in flight
-      u64 buf = 0;
-      int avail = 0;
-      bool more = true;
-      while (more) {
+    typedef CursorGeom<kLutCBits, 1> G;
+    u64 u, ulast;
+    u32 acc;
+    if (bulk && pos < end && cursor_plan<kLutCBits, 1>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
+      const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
+      const u64 umax = (g.readable >> 5) - 1;
+      Unit8 cur = ldg_unit(g.payload + 32 * u, aligned32);
+      Unit8 nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);  // one unit in flight
+      const smem_addr_t lut = smem_addr(s.lutC);
+      u32 hi, lo = 0;
+      while (true) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (u32(k) < k0) continue;
-          const u32 w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
-          buf |= u64(be32(w)) << (32 - avail);
-          avail += 32;
-          if (drop) buf <<= drop, avail -= int(drop), drop = 0;
-          while (avail >= 32 && pos <= last) {
-            const u32 win = u32(buf >> 32);
-            const u32 e = s.lutC[win >> (32 - kLutCBits)];
-            u32 len;
-            if (e) {
-              len = e & 15u;
-              count += e >> 4;
-            } else {  // first codeword longer than the table window, or the end mark
-              u32 sym;
-              decode_one(s.canon, s.lut1, win, sym, len);
-              if (sym == u32(GH_EOF_SYMBOL)) {
-                if (!neof) first_eof = count;
-                ++neof;
-              }
-              ++count;
+        for (int k = 0; k < kUnitWords; ++k) {
+          const u32 next_raw = k + 1 < kUnitWords ? cur.w[(k + 1) % kUnitWords] : nxt.w[0];
+          hi = lo;
+          lo = be32(cur.w[k]);
+          acc += 32u;
+          while ((acc & kCurBusy) == 0u) {
+            do {
+              const u32 x = __funnelshift_r(lo, hi, acc);
+              acc += lds_u16(lut, x & G::kMask);
+            } while ((acc & kCurBusy) == 0u);
+            if ((acc & kCurMissBit) == 0u) break;
+            // first codeword longer than the table window, or the end mark
+            acc -= kLutMiss;
+            u32 sym, len;
+            decode_one(s.canon, s.lut1, cursor_window32<kLutCBits, 1>(hi, lo, next_raw, acc), sym, len);
+            if (sym == u32(GH_EOF_SYMBOL)) {
+              if (!neof) first_eof = count + (acc >> kCurShift);
+              ++neof;
             }
-            pos += len;
-            buf <<= len;
-            avail -= int(len);
-          }
-          if (pos > last) {
-            more = false;
-            break;
+            acc += (1u << kCurShift) - len;
           }
         }
-        k0 = 0;
-        if (!more) break;
-        ++v;
-        if (v + 2 >= full_vecs) break;  // the last vectors of the payload go through the bounds-checked reader
+        count += acc >> kCurShift;
+        acc &= kCurFieldMask;
+        if (u == ulast) break;
+        ++u;
         cur = nxt;
-        nxt = nxt2;
-        nxt2 = ldg128(vp + v + 2);
+        nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
       }
+      pos = u32(cursor_position<kLutCBits, 1>(ulast, acc) - start);
     }
   }
   // (a') whatever the bulk loop left (payload tail), same steps through the bounds-checked reader
@@ -365,11 +423,9 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   r.seek(g.payload, g.readable, start + pos);
   while (bulk && pos <= last) {
     const u32 win = r.window();
-    const u32 e = s.lutC[win >> (32 - kLutCBits)];
-    u32 len;
-    if (e) {
-      len = e & 15u;
-      count += e >> 4;
+    u32 len, cnt;
+    if (lutc_hit(s.lutC[win >> (32 - kLutCBits)], len, cnt)) {
+      count += cnt;
     } else {
       u32 sym;
       decode_one(s.canon, s.lut1, win, sym, len);
@@ -408,11 +464,7 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
 __global__ void __launch_bounds__(kDecThreads)
 dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
   __shared__ SmemSpeculate s;
-  load_canon(s.canon, ws.tables);
-  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
-    reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
-  for (unsigned i = threadIdx.x; i < (1u << kLutCBits) / 16; i += kDecThreads)
-    reinterpret_cast<uint4*>(s.lutC)[i] = reinterpret_cast<const uint4*>(ws.lutC)[i];
+  load_speculate_tables(s, ws);
   __syncthreads();
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
   u64 mine = 0;
@@ -446,13 +498,11 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
         merged = true;
         break;
       }
-      u32 sym, len;
+      u32 sym, len, cnt;
       if (pos_a < pos_b) {
         const u32 win = ra.window();
-        const u32 e = (bulk && pos_a <= last) ? u32(s.lutC[win >> (32 - kLutCBits)]) : 0u;
-        if (e) {
-          len = e & 15u;
-          steps_a += e >> 4;
+        if (bulk && pos_a <= last && lutc_hit(s.lutC[win >> (32 - kLutCBits)], len, cnt)) {
+          steps_a += cnt;
         } else {
           decode_one(s.canon, s.lut1, win, sym, len);
           ++steps_a;
@@ -462,10 +512,8 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
         ra.consume(len);
       } else {
         const u32 win = rb.window();
-        const u32 e = (bulk && pos_b <= last) ? u32(s.lutC[win >> (32 - kLutCBits)]) : 0u;
-        if (e) {
-          len = e & 15u;
-          steps_b += e >> 4;
+        if (bulk && pos_b <= last && lutc_hit(s.lutC[win >> (32 - kLutCBits)], len, cnt)) {
+          steps_b += cnt;
         } else {
           decode_one(s.canon, s.lut1, win, sym, len);
           if (sym == u32(GH_EOF_SYMBOL)) {
@@ -537,11 +585,7 @@ dec_locate_eof_kernel(DecGeometry g, DecWorkspace ws) {
     if (threadIdx.x == 0) ws.ctl->eof_prefix = known;
     return;
   }
-  load_canon(s.canon, ws.tables);
-  for (unsigned k = threadIdx.x; k < (1u << kLut1Bits) / 2; k += kDecThreads)
-    reinterpret_cast<u32*>(s.lut1)[k] = reinterpret_cast<const u32*>(ws.lut1)[k];
-  for (unsigned k = threadIdx.x; k < (1u << kLutCBits) / 16; k += kDecThreads)
-    reinterpret_cast<uint4*>(s.lutC)[k] = reinterpret_cast<const uint4*>(ws.lutC)[k];
+  load_speculate_tables(s, ws);
   __syncthreads();
   if (threadIdx.x != 0) return;
   const u64 st = ws.sub[i];
@@ -551,11 +595,9 @@ dec_locate_eof_kernel(DecGeometry g, DecWorkspace ws) {
   r.seek(g.payload, g.readable, u64(i) * u64(g.sub_bytes) * 8 + pos);
   while (pos < end) {
     const u32 win = r.window();
-    const u32 e = s.lutC[win >> (32 - kLutCBits)];
-    u32 len;
-    if (e) {  // whole codewords, never the end mark
-      len = e & 15u;
-      count += e >> 4;
+    u32 len, cnt;
+    if (lutc_hit(s.lutC[win >> (32 - kLutCBits)], len, cnt)) {  // whole codewords, never the end mark
+      count += cnt;
     } else {
       u32 sym;
       decode_one(s.canon, s.lut1, win, sym, len);
@@ -628,22 +670,73 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
 }
 
 // ---- K7: final decode from the exact entries ------------------------------------------------------------------
-// Up to 3 codewords per lookup (13-bit window); symbols are collected 8 at a time in a 64-bit register and two
-// such registers leave as one 128-bit store (the first few symbols go out as bytes to reach alignment).
+// The cursor reader with the 13-bit table lutW: one LDS.64 yields the cursor/fill addend and up to 4 symbols.
+// `acc` carries, above the cursor byte, the number of output BITS produced so far (modulo 2^24), so the same IADD
+// that moves the cursor also advances the output fill; the symbols are shifted to the fill position (SHF takes
+// acc >> 9 modulo 32) and OR-ed into the word being assembled. A word is complete when bit 5 of the fill flips
+// (it joins a four-register queue), four words are complete when bit 7 flips (one 128-bit store): both are one
+// LOP3 on acc ^ acc_before. Everything between two stores is predicated straight-line code.
 struct SmemWrite {
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
-  u32 lutW[1 << kLutWBits];
+  uint2 lutW[1 << kLutWBits];
   u32 warp_total[kDecThreads / 32];
 };
 
+// Output queue of the write loop, branch-free: if `word_done`, the assembled word `merged` is shifted into the
+// four-register queue and `spill` opens the next word; if `group_done`, the queue leaves as one 128-bit store and
+// the destination advances. (Written as predicated PTX: as C++ branches the compiler turns these few moves into
+// divergent control flow that every warp then walks on almost every iteration.)
+__device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32& q3, u32& part, u32 merged, u32 spill,
+                                                 u32 word_done, u32 group_done, uint8_t*& gdst) {
+#ifdef GH_EMUL
+  if (word_done) {
+    q0 = q1, q1 = q2, q2 = q3, q3 = merged;
+    part = spill;
+  } else {
+    part = merged;
+  }
+  if (group_done) {
+    *reinterpret_cast<uint4*>(gdst) = make_uint4(q0, q1, q2, q3);
+    gdst += 16;
+  }
+#else
+  asm volatile(
+      "{\n"
+      " .reg .pred pw, pg;\n"
+      " setp.ne.u32 pw, %8, 0;\n"
+      " setp.ne.u32 pg, %9, 0;\n"
+      " selp.u32 %0, %1, %0, pw;\n"
+      " selp.u32 %1, %2, %1, pw;\n"
+      " selp.u32 %2, %3, %2, pw;\n"
+      " selp.u32 %3, %6, %3, pw;\n"
+      " selp.u32 %4, %7, %6, pw;\n"
+      " @pg st.global.v4.u32 [%5], {%0, %1, %2, %3};\n"
+      " @pg add.u64 %5, %5, 16;\n"
+      "}\n"
+      : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "=&r"(part), "+l"(gdst)
+      : "r"(merged), "r"(spill), "r"(word_done), "r"(group_done)
+      : "memory");
+#endif
+}
+
+// bytes [from, to) of the 16-byte group (q0, q1, q2, q3) -> dst[from .. to): the unaligned head and the tail of a
+// lane's output (once per subsequence each)
+__device__ __noinline__ void store_group_bytes(uint8_t* dst, u32 q0, u32 q1, u32 q2, u32 q3, u32 from, u32 to) {
+  for (u32 b = from; b < to; ++b) {
+    const u32 w = (b >> 2) == 0 ? q0 : (b >> 2) == 1 ? q1 : (b >> 2) == 2 ? q2 : q3;
+    dst[b] = uint8_t(w >> (8 * (b & 3)));
+  }
+}
+
 __global__ void __launch_bounds__(kDecThreads, GH_DEC_W_BLOCKS)
 dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
-  __shared__ SmemWrite s;
+  GH_DYNAMIC_SMEM(smem_raw);
+  SmemWrite& s = *reinterpret_cast<SmemWrite*>(smem_raw);
   load_canon(s.canon, ws.tables);
-  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 2; i += kDecThreads)
-    reinterpret_cast<u32*>(s.lut1)[i] = reinterpret_cast<const u32*>(ws.lut1)[i];
-  for (unsigned i = threadIdx.x; i < (1u << kLutWBits) / 4; i += kDecThreads)
+  for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 8; i += kDecThreads)
+    reinterpret_cast<uint4*>(s.lut1)[i] = reinterpret_cast<const uint4*>(ws.lut1)[i];
+  for (unsigned i = threadIdx.x; i < (1u << kLutWBits) / 2; i += kDecThreads)
     reinterpret_cast<uint4*>(s.lutW)[i] = reinterpret_cast<const uint4*>(ws.lutW)[i];
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const u64 i = u64(blockIdx.x) * kDecThreads + t;
@@ -667,11 +760,13 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   if (u64(remaining) > out_cap - o) remaining = u32(out_cap - o);
 
   const u64 start = i * u64(g.sub_bytes) * 8;
+  const u32 end = u32(sub_end_bits(g, i));
   u32 pos = st_entry(st);  // bits of the subsequence consumed so far
   uint8_t* dst = out + o;
   u32 sym, len;
-  // head: single symbols up to the first 16-byte boundary of the output
-  {
+  // head: single symbols up to the first 16-byte boundary of the output (the bytes before it belong to the
+  // previous lane), so that the bulk loop below only ever issues whole aligned 128-bit stores
+  if (reinterpret_cast<uintptr_t>(dst) & 15) {
     BitReader r;
     r.seek(g.payload, g.readable, start + pos);
     while (remaining && (reinterpret_cast<uintptr_t>(dst) & 15)) {
@@ -682,135 +777,88 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
       --remaining;
     }
   }
-  // body: one table lookup per iteration for every lane. Everything that happens only now and then per lane
-  // (32-bit refill, 128-bit reload, retiring 8 collected symbols, every second retirement a 128-bit store) is
-  // short straight-line code: with 32 lanes out of step, "now and then per lane" is "every iteration per warp",
-  // so the loop is written to make those paths cheap rather than rare.
-  u64 acc = 0, held = 0;
-  u32 nacc = 0;  // symbols in acc (0..7 between iterations), first symbol in the lowest byte
-  bool have_held = false;
-  auto emit = [&](u64 syms, u32 n) {  // n <= 6 symbols, first in the lowest byte
-    const u32 sh = nacc * 8;
-    acc |= syms << sh;
-    nacc += n;
-    if (nacc >= 8) {
-      const u64 spill = sh ? syms >> (64 - sh) : 0ull;  // bytes that did not fit
-      if (have_held) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(u32(held), u32(held >> 32), u32(acc), u32(acc >> 32));
-        dst += 16;
-      } else {
-        held = acc;
-      }
-      have_held = !have_held;
-      acc = spill;
-      nacc -= 8;
-    }
-  };
+  // bulk: every codeword that starts before `end` belongs to this lane (that is what `count` counted), so the loop
+  // is bounded by the bit position alone; a lane whose output was clipped by out_cap takes the slow path only.
   {
-    const u64 bit0 = start + pos;
-    const u64 v0 = bit0 >> 7;
-    const u64 full_vecs = g.readable >> 4;
-    if (remaining >= u32(kLutWMaxSyms) && v0 + 2 < full_vecs) {
-      const uint4* vp = reinterpret_cast<const uint4*>(g.payload) + v0;  // vector indices below are relative to v0
-      uint4 cur = ldg128(vp), ahead = ldg128(vp + 1);
-      u32 vnext = 2;  // next vector to request
-      const u64 span = full_vecs - v0;
-      const u32 vend = span > 0x7fffffffull ? 0x7fffffffu : u32(span);  // vectors that may be requested
-      u32 w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
-      const u32 skip = u32(bit0 >> 5) & 3u;
-      for (u32 k = 0; k < skip; ++k) w0 = w1, w1 = w2, w2 = w3;
-      u32 left = 4 - skip;
-      u64 buf = 0;
-      int avail = 0;
-      auto push = [&]() {
-        buf |= u64(be32(w0)) << (32 - avail);
-        avail += 32;
-        w0 = w1, w1 = w2, w2 = w3;
-        if (--left == 0) {
-          w0 = ahead.x, w1 = ahead.y, w2 = ahead.z, w3 = ahead.w;
-          left = 4;
-          ahead = ldg128(vp + vnext);  // vnext < vend is the loop condition
-          ++vnext;
-        }
+    typedef CursorGeom<kLutWBits, 3> G;
+    u64 u, ulast;
+    u32 acc;
+    if (remaining && u64(count) <= out_cap - o && pos < end &&
+        cursor_plan<kLutWBits, 3>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
+      const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
+      const u64 umax = (g.readable >> 5) - 1;
+      Unit8 cur = ldg_unit(g.payload + 32 * u, aligned32);
+      Unit8 nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+      const smem_addr_t lut = smem_addr(s.lutW);
+      uint8_t* gdst = dst;  // 16-byte aligned
+      u32 q0 = 0, q1 = 0, q2 = 0, q3 = 0, part = 0;
+      u32 hi, lo = 0;
+      bool stop = false;  // the end mark was met (the subsequence that ends the stream)
+      auto append = [&](u32 addend, u32 syms) {
+        const u32 fill = acc >> kCurShift;  // output bits so far; SHF uses it modulo 32
+        const u32 merged = part | __funnelshift_l(0u, syms, fill);
+        const u32 spill = __funnelshift_l(syms, 0u, fill);
+        const u32 next = acc + addend;
+        const u32 flipped = next ^ acc;
+        acc = next;
+        // a word is complete when bit 5 of the fill flipped: it joins the queue, the overflow opens the next one;
+        // four words are complete when bit 7 flipped: one 128-bit store. Predicated, no branches.
+        queue_push_store(q0, q1, q2, q3, part, merged, spill, flipped & (32u << kCurShift),
+                         flipped & (128u << kCurShift), gdst);
       };
-      push();
-      push();
-      {
-        const u32 drop = u32(bit0) & 31u;
-        buf <<= drop;
-        avail -= int(drop);
-        if (avail < 32) push();
-      }
-      // two lookups per iteration, one refill check and one retirement check for both: a table hit needs at most
-      // 13 valid bits, so after the first hit (>= 32 - 13 = 19 bits left) the second can go ahead unrefilled
-      while (remaining >= 2u * kLutWMaxSyms && vnext < vend) {
-        u32 win = u32(buf >> 32);
-        u32 e = s.lutW[win >> (32 - kLutWBits)];
-        u32 n, syms;
-        if (e) {
-          len = e & 15u;
-          n = (e >> 4) & 3u;
-          syms = e >> 8;
-        } else {  // codeword longer than 13 bits (the end mark cannot occur: the count stops before it)
-          decode_one(s.canon, s.lut1, win, sym, len);
-          n = 1;
-          syms = sym & 0xffu;
+      while (true) {
+#pragma unroll
+        for (int k = 0; k < kUnitWords; ++k) {
+          const u32 next_raw = k + 1 < kUnitWords ? cur.w[(k + 1) % kUnitWords] : nxt.w[0];
+          hi = lo;
+          lo = be32(cur.w[k]);
+          acc += 32u;
+          while ((acc & kCurBusy) == 0u) {
+            do {
+              const u32 x = __funnelshift_r(lo, hi, acc);
+              const uint2 e = lds_v2(lut, x & G::kMask);
+              append(e.x, e.y);
+            } while ((acc & kCurBusy) == 0u);
+            if ((acc & kCurMissBit) == 0u) break;
+            // codeword longer than the table window, or the end mark (only in the subsequence that ends the stream)
+            acc -= kLutMiss;
+            decode_one(s.canon, s.lut1, cursor_window32<kLutWBits, 3>(hi, lo, next_raw, acc), sym, len);
+            if (sym == u32(GH_EOF_SYMBOL)) {
+              stop = true;
+              acc = (acc & ~kCurFieldMask) | 192u;  // stays below the allowed range for the rest of this unit
+              break;
+            }
+            append((8u << kCurShift) - len, sym);
+          }
         }
-        pos += len;
-        buf <<= len;
-        avail -= int(len);
-        if (avail < int(kLutWBits)) push();  // only after a long codeword
-        win = u32(buf >> 32);
-        e = s.lutW[win >> (32 - kLutWBits)];
-        u32 n2, syms2;
-        if (e) {
-          len = e & 15u;
-          n2 = (e >> 4) & 3u;
-          syms2 = e >> 8;
-        } else {
-          if (avail < 32) push();
-          win = u32(buf >> 32);
-          decode_one(s.canon, s.lut1, win, sym, len);
-          n2 = 1;
-          syms2 = sym & 0xffu;
-        }
-        pos += len;
-        buf <<= len;
-        avail -= int(len);
-        if (avail < 32) push();
-        remaining -= n + n2;
-        emit(u64(syms) | (u64(syms2) << (8 * n)), n + n2);
+        if (stop || u == ulast) break;
+        ++u;
+        cur = nxt;
+        nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
       }
+      // drain: the open 16-byte group holds (fill mod 128) bits: completed words at the top of the queue, then `part`
+      const u32 fill = acc >> kCurShift;
+      const u32 open_bits = fill & 127u;
+      const u32 done_words = open_bits >> 5;
+      for (u32 k = done_words; k < 4; ++k) q0 = q1, q1 = q2, q2 = q3, q3 = (k == done_words ? part : 0u);
+      store_group_bytes(gdst, q0, q1, q2, q3, 0, open_bits >> 3);
+      const u64 emitted = u64(gdst - dst) + (open_bits >> 3);
+      dst += emitted;
+      remaining = stop ? 0u : remaining - u32(emitted);
+      pos = u32(cursor_position<kLutWBits, 3>(ulast, acc) - start);
     }
   }
-  // what the bulk loop left (payload tail or the last couple of symbols): bounds-checked reader from `pos`
-  BitReader r;
-  r.seek(g.payload, g.readable, start + pos);
-  while (remaining >= u32(kLutWMaxSyms)) {
-    const u32 win = r.window();
-    const u32 e = s.lutW[win >> (32 - kLutWBits)];
-    u32 n, syms;
-    if (e) {
-      len = e & 15u;
-      n = (e >> 4) & 3u;
-      syms = e >> 8;
-    } else {
-      decode_one(s.canon, s.lut1, win, sym, len);
-      n = 1;
-      syms = sym & 0xffu;
+  // what the bulk loop left (the last few bits of the subsequence, the payload tail, clipped output): one codeword
+  // at a time through the bounds-checked reader from `pos`
+  if (remaining) {
+    BitReader r;
+    r.seek(g.payload, g.readable, start + pos);
+    while (remaining) {
+      decode_one(s.canon, s.lut1, r.window(), sym, len);
+      r.consume(len);
+      *dst++ = uint8_t(sym);
+      --remaining;
     }
-    r.consume(len);
-    remaining -= n;
-    emit(syms, n);
-  }
-  // drain what is collected, then the last few symbols one by one
-  if (have_held) *reinterpret_cast<uint2*>(dst) = make_uint2(u32(held), u32(held >> 32)), dst += 8;
-  for (u32 k = 0; k < nacc; ++k) *dst++ = uint8_t(acc >> (8 * k));
-  while (remaining) {
-    decode_one(s.canon, s.lut1, r.window(), sym, len);
-    r.consume(len);
-    *dst++ = uint8_t(sym);
-    --remaining;
   }
 }
 
@@ -1077,6 +1125,15 @@ static int pipeline_choice() {
   return g_pipeline;
 }
 
+static int set_write_attrs() {  // SmemWrite exceeds the 48 KB a kernel gets without opting in
+  static bool done = false;
+  if (!done) {
+    GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(SmemWrite))));
+    done = true;
+  }
+  return GH_OK;
+}
+
 static int set_fine_attrs() {  // opt-in to > 48 KB of dynamic shared memory for the kernels that need it
   static bool done = false;
   if (!done) {
@@ -1101,8 +1158,8 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_tables = 0;
   L.off_lut1 = up(sizeof(DecodeTables));
   L.off_lutC = L.off_lut1 + up(sizeof(uint16_t) << kLut1Bits);
-  L.off_lutW = L.off_lutC + up(sizeof(uint8_t) << kLutCBits);
-  L.off_lutP = L.off_lutW + up(sizeof(u32) << kLutWBits);
+  L.off_lutW = L.off_lutC + up(sizeof(uint16_t) << kLutCBits);
+  L.off_lutP = L.off_lutW + up(sizeof(uint2) << kLutWBits);
   L.off_ctl = L.off_lutP + up(sizeof(u32) << kLutPBits);
   L.off_sub = L.off_ctl + 256;
   L.off_neof = L.off_sub + up(size_t(max_sub) * 8);
@@ -1120,8 +1177,8 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   DecWorkspace w;
   w.tables = reinterpret_cast<const DecodeTables*>(p + L.off_tables);
   w.lut1 = reinterpret_cast<const uint16_t*>(p + L.off_lut1);
-  w.lutC = reinterpret_cast<const uint8_t*>(p + L.off_lutC);
-  w.lutW = reinterpret_cast<const u32*>(p + L.off_lutW);
+  w.lutC = reinterpret_cast<const uint16_t*>(p + L.off_lutC);
+  w.lutW = reinterpret_cast<const uint2*>(p + L.off_lutW);
   w.lutP = reinterpret_cast<const u32*>(p + L.off_lutP);
   w.ctl = reinterpret_cast<DecControl*>(p + L.off_ctl);
   w.sub = reinterpret_cast<u64*>(p + L.off_sub);
@@ -1180,7 +1237,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     if (rc != GH_OK) return rc;
     GH_CUDA_TRY(cudaMemcpyAsync(const_cast<DecodeTables*>(ws.tables), &tables, sizeof(tables), cudaMemcpyHostToDevice, stream));
     GH_LAUNCH(dec_build_luts_kernel, (1u << kLutCBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
-              const_cast<uint8_t*>(ws.lutC), const_cast<u32*>(ws.lutW), const_cast<u32*>(ws.lutP));
+              const_cast<uint16_t*>(ws.lutC), const_cast<uint2*>(ws.lutW), const_cast<u32*>(ws.lutP));
     const bool slow_code = code->max_len - code->min_len <= 1;
     // measured (profiles/r1i): the fine pipeline is not yet faster than the coarse one, so it is opt-in
     fine = pipeline_choice() == 2;
@@ -1288,8 +1345,10 @@ static int decode_write_impl(const DecGeometry& g, bool fine, uint8_t* d_out, u6
     const unsigned blocks = unsigned((g.n_sub + kFineWarps - 1) / kFineWarps);
     GH_LAUNCH(dec_fine_write_kernel, blocks, kFineWarps * 32, sizeof(SmemFineWrite), stream, g, d_out, out_cap, ws);
   } else {
+    int rc = set_write_attrs();
+    if (rc != GH_OK) return rc;
     const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
-    GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, 0, stream, g, d_out, out_cap, ws);
+    GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, sizeof(SmemWrite), stream, g, d_out, out_cap, ws);
   }
   return check_launch();
 }

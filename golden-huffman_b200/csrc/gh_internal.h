@@ -15,10 +15,12 @@ namespace gh {
 //   lut1  2^12 x u16   one codeword per lookup: (symbol << 6) | length, 0 = codeword longer than 12 bits.
 //                      The device analogue of TableCanonicalHuffDecoder::lookup_table_
 //                      (reference include/canonical_huff_encoder.cc:466-516) with the symbol folded in.
-//   lutC  2^14 x u8    as many whole codewords as fit in 14 bits (never the end mark): (count << 4) | total length,
-//                      0 = the first codeword does not fit or is the end mark. Used where only counts matter.
-//   lutW  2^13 x u32   up to 3 whole codewords in 13 bits: total length | count << 4 | symbols << 8 (first symbol
-//                      in the lowest byte), 0 = first codeword does not fit or is the end mark.
+//   lutC  2^14 x u16   as many whole codewords as fit in 14 bits (never the end mark), as ONE addend for the
+//                      decoder's cursor word:  (codewords << 10) - total length.  kLutMiss = the first codeword does
+//                      not fit or is the end mark. Used where only counts matter.
+//   lutW  2^13 x u32x2 up to 4 whole codewords in 13 bits: .x = (8 * codewords << 10) - total length (one addend that
+//                      advances the output fill in bits and moves the cursor), .y = the symbols, first in the lowest
+//                      byte. .x = kLutMiss when the first codeword does not fit or is the end mark.
 //   lutP  2^12 x u32   one or two whole codewords in 12 bits, with the first length kept so a step can stop after
 //                      the first: total length | count << 4 | first length << 6 | symbol 1 << 16 | symbol 2 << 24,
 //                      0 = first codeword does not fit or is the end mark. Used by the warp-cooperative writer.
@@ -32,7 +34,9 @@ constexpr int kLutPBits = 12;
 #endif
 constexpr int kLutCBits = GH_LUTC_BITS;
 constexpr int kLutWBits = GH_LUTW_BITS;
-constexpr int kLutWMaxSyms = 3;
+constexpr int kLutWMaxSyms = 4;
+constexpr uint32_t kLutMiss = 32;  // see the cursor reader in gh_decode.cu
+constexpr int kCurShift = 10;      // table addends count above a 10-bit cursor field
 
 struct DecodeTables {
   uint32_t first_code_lj[34];  // first_code_[len] << (32 - len), "left-justified" as in FastCanonicalHuffDecoder

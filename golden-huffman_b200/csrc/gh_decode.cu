@@ -137,6 +137,13 @@ __device__ __forceinline__ void decode_one(const SmemCanon& s, const uint16_t* l
   if (len == 0) canon_search(s, window, kLut1Bits + 1, sym, len);
 }
 
+// out-of-line variant for the bulk loops' miss paths (rare; keeps the unrolled loop bodies small): (symbol << 8) | length
+__device__ __noinline__ u32 decode_one_packed(const SmemCanon* s, const uint16_t* lut1, u32 window) {
+  u32 sym, len;
+  decode_one(*s, lut1, window, sym, len);
+  return (sym << 8) | len;
+}
+
 // ---- K5 prologue: expand the canonical tables into the lookup tables, on the device -------------------------
 // thread w handles window value w of each table it is in range for
 __global__ void __launch_bounds__(256)
@@ -380,16 +387,15 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
     if (bulk && pos < end && cursor_plan<kLutCBits, 1>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
       const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
       const u64 umax = (g.readable >> 5) - 1;
-      Unit8 cur = ldg_unit(g.payload + 32 * u, aligned32);
-      Unit8 nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);  // one unit in flight
       const smem_addr_t lut = smem_addr(s.lutC);
       u32 hi, lo = 0;
-      while (true) {
+      // one 32-byte unit: eight word steps
+      auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {
 #pragma unroll
         for (int k = 0; k < kUnitWords; ++k) {
-          const u32 next_raw = k + 1 < kUnitWords ? cur.w[(k + 1) % kUnitWords] : nxt.w[0];
+          const u32 next_raw = k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : next_unit_word0;
           hi = lo;
-          lo = be32(cur.w[k]);
+          lo = be32(cu.w[k]);
           acc += 32u;
           while ((acc & kCurBusy) == 0u) {
             do {
@@ -399,21 +405,28 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
             if ((acc & kCurMissBit) == 0u) break;
             // first codeword longer than the table window, or the end mark
             acc -= kLutMiss;
-            u32 sym, len;
-            decode_one(s.canon, s.lut1, cursor_window32<kLutCBits, 1>(hi, lo, next_raw, acc), sym, len);
-            if (sym == u32(GH_EOF_SYMBOL)) {
+            const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutCBits, 1>(hi, lo, next_raw, acc));
+            if ((sl >> 8) == u32(GH_EOF_SYMBOL)) {
               if (!neof) first_eof = count + (acc >> kCurShift);
               ++neof;
             }
-            acc += (1u << kCurShift) - len;
+            acc += (1u << kCurShift) - (sl & 0xffu);
           }
         }
         count += acc >> kCurShift;
         acc &= kCurFieldMask;
+      };
+      // two unit buffers that swap roles, so the unit in flight is never copied (a copy would wait for the load)
+      Unit8 ua = ldg_unit(g.payload + 32 * u, aligned32), ub;
+      while (true) {
+        ub = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        walk_unit(ua, ub.w[0]);
         if (u == ulast) break;
         ++u;
-        cur = nxt;
-        nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        ua = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        walk_unit(ub, ua.w[0]);
+        if (u == ulast) break;
+        ++u;
       }
       pos = u32(cursor_position<kLutCBits, 1>(ulast, acc) - start);
     }
@@ -684,11 +697,14 @@ struct SmemWrite {
 };
 
 // Output queue of the write loop, branch-free: if `word_done`, the assembled word `merged` is shifted into the
-// four-register queue and `spill` opens the next word; if `group_done`, the queue leaves as one 128-bit store and
-// the destination advances. (Written as predicated PTX: as C++ branches the compiler turns these few moves into
-// divergent control flow that every warp then walks on almost every iteration.)
+// four-register queue and `spill` opens the next word; if `group_done`, the queue leaves as one 128-bit store to
+// the lane's 16-byte-aligned destination (ghi:glo), which then advances. Written as predicated PTX: as C++
+// branches the compiler turns these few moves into divergent control flow that every warp then walks on almost
+// every iteration; and as predicated MOVs (not SEL) so that ptxas may place them on the FMA pipe -- the loop's
+// shifts and logic ops already fill the ALU pipe (each pipe issues a warp instruction every other cycle).
 __device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32& q3, u32& part, u32 merged, u32 spill,
-                                                 u32 word_done, u32 group_done, uint8_t*& gdst) {
+                                                 u32 word_done, u32 group_done, u32& glo, u32& ghi, u32 one) {
+  (void)one;  // a register holding 1 that ptxas cannot see through: `x * one` is a move on the FMA pipe
 #ifdef GH_EMUL
   if (word_done) {
     q0 = q1, q1 = q2, q2 = q3, q3 = merged;
@@ -697,25 +713,30 @@ __device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32&
     part = merged;
   }
   if (group_done) {
-    *reinterpret_cast<uint4*>(gdst) = make_uint4(q0, q1, q2, q3);
-    gdst += 16;
+    const u64 a = (u64(ghi) << 32) | glo;
+    *reinterpret_cast<uint4*>(a) = make_uint4(q0, q1, q2, q3);
+    glo = u32(a + 16), ghi = u32((a + 16) >> 32);
   }
 #else
+  part = merged;
   asm volatile(
       "{\n"
       " .reg .pred pw, pg;\n"
+      " .reg .u64 a;\n"
       " setp.ne.u32 pw, %8, 0;\n"
       " setp.ne.u32 pg, %9, 0;\n"
-      " selp.u32 %0, %1, %0, pw;\n"
-      " selp.u32 %1, %2, %1, pw;\n"
-      " selp.u32 %2, %3, %2, pw;\n"
-      " selp.u32 %3, %6, %3, pw;\n"
-      " selp.u32 %4, %7, %6, pw;\n"
-      " @pg st.global.v4.u32 [%5], {%0, %1, %2, %3};\n"
-      " @pg add.u64 %5, %5, 16;\n"
+      " @pw mad.lo.u32 %0, %1, %10, 0;\n"
+      " @pw mad.lo.u32 %1, %2, %10, 0;\n"
+      " @pw mad.lo.u32 %2, %3, %10, 0;\n"
+      " @pw mad.lo.u32 %3, %4, %10, 0;\n"
+      " @pw mov.u32 %4, %7;\n"
+      " mov.b64 a, {%5, %6};\n"
+      " @pg st.global.v4.u32 [a], {%0, %1, %2, %3};\n"
+      " @pg add.cc.u32 %5, %5, 16;\n"
+      " @pg addc.u32 %6, %6, 0;\n"
       "}\n"
-      : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "=&r"(part), "+l"(gdst)
-      : "r"(merged), "r"(spill), "r"(word_done), "r"(group_done)
+      : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(part), "+r"(glo), "+r"(ghi)
+      : "r"(spill), "r"(word_done), "r"(group_done), "r"(one)
       : "memory");
 #endif
 }
@@ -787,15 +808,15 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         cursor_plan<kLutWBits, 3>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
       const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
       const u64 umax = (g.readable >> 5) - 1;
-      Unit8 cur = ldg_unit(g.payload + 32 * u, aligned32);
-      Unit8 nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
       const smem_addr_t lut = smem_addr(s.lutW);
-      uint8_t* gdst = dst;  // 16-byte aligned
+      // destination of the next 128-bit store (16-byte aligned), as two words so the advance can be predicated
+      u32 glo = u32(reinterpret_cast<uintptr_t>(dst)), ghi = u32(u64(reinterpret_cast<uintptr_t>(dst)) >> 32);
+      const u32 one = blockDim.x / kDecThreads;  // 1, but not to ptxas: `x * one` stays a move on the FMA pipe
       u32 q0 = 0, q1 = 0, q2 = 0, q3 = 0, part = 0;
       u32 hi, lo = 0;
       bool stop = false;  // the end mark was met (the subsequence that ends the stream)
       auto append = [&](u32 addend, u32 syms) {
-        const u32 fill = acc >> kCurShift;  // output bits so far; SHF uses it modulo 32
+        const u32 fill = __umulhi(acc, 1u << (32 - kCurShift));  // acc >> kCurShift on the FMA pipe; SHF uses it modulo 32
         const u32 merged = part | __funnelshift_l(0u, syms, fill);
         const u32 spill = __funnelshift_l(syms, 0u, fill);
         const u32 next = acc + addend;
@@ -804,14 +825,14 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         // a word is complete when bit 5 of the fill flipped: it joins the queue, the overflow opens the next one;
         // four words are complete when bit 7 flipped: one 128-bit store. Predicated, no branches.
         queue_push_store(q0, q1, q2, q3, part, merged, spill, flipped & (32u << kCurShift),
-                         flipped & (128u << kCurShift), gdst);
+                         flipped & (128u << kCurShift), glo, ghi, one);
       };
-      while (true) {
+      auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {
 #pragma unroll
         for (int k = 0; k < kUnitWords; ++k) {
-          const u32 next_raw = k + 1 < kUnitWords ? cur.w[(k + 1) % kUnitWords] : nxt.w[0];
+          const u32 next_raw = k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : next_unit_word0;
           hi = lo;
-          lo = be32(cur.w[k]);
+          lo = be32(cu.w[k]);
           acc += 32u;
           while ((acc & kCurBusy) == 0u) {
             do {
@@ -822,25 +843,34 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
             if ((acc & kCurMissBit) == 0u) break;
             // codeword longer than the table window, or the end mark (only in the subsequence that ends the stream)
             acc -= kLutMiss;
-            decode_one(s.canon, s.lut1, cursor_window32<kLutWBits, 3>(hi, lo, next_raw, acc), sym, len);
-            if (sym == u32(GH_EOF_SYMBOL)) {
+            const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutWBits, 3>(hi, lo, next_raw, acc));
+            if ((sl >> 8) == u32(GH_EOF_SYMBOL)) {
               stop = true;
               acc = (acc & ~kCurFieldMask) | 192u;  // stays below the allowed range for the rest of this unit
               break;
             }
-            append((8u << kCurShift) - len, sym);
+            append((8u << kCurShift) - (sl & 0xffu), sl >> 8);
           }
         }
+      };
+      // two unit buffers that swap roles, so the unit in flight is never copied (a copy would wait for the load)
+      Unit8 ua = ldg_unit(g.payload + 32 * u, aligned32), ub;
+      while (true) {
+        ub = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        walk_unit(ua, ub.w[0]);
         if (stop || u == ulast) break;
         ++u;
-        cur = nxt;
-        nxt = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        ua = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        walk_unit(ub, ua.w[0]);
+        if (stop || u == ulast) break;
+        ++u;
       }
       // drain: the open 16-byte group holds (fill mod 128) bits: completed words at the top of the queue, then `part`
       const u32 fill = acc >> kCurShift;
       const u32 open_bits = fill & 127u;
       const u32 done_words = open_bits >> 5;
       for (u32 k = done_words; k < 4; ++k) q0 = q1, q1 = q2, q2 = q3, q3 = (k == done_words ? part : 0u);
+      uint8_t* const gdst = reinterpret_cast<uint8_t*>((u64(ghi) << 32) | glo);
       store_group_bytes(gdst, q0, q1, q2, q3, 0, open_bits >> 3);
       const u64 emitted = u64(gdst - dst) + (open_bits >> 3);
       dst += emitted;

@@ -226,6 +226,7 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
   uint64_t v = (uint64_t(hi) << 32) | lo;
   return unsigned(v >> (shift & 31));
 }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return unsigned((uint64_t(a) * b) >> 32); }
 static inline unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
 

@@ -141,6 +141,9 @@ __device__ __forceinline__ u32 lds_u16(smem_addr_t base, u32 byte_off) {
 __device__ __forceinline__ uint2 lds_v2(smem_addr_t base, u32 byte_off) {
   return *reinterpret_cast<const uint2*>(base + byte_off);
 }
+__device__ __forceinline__ u32 lds_u32(smem_addr_t base, u32 byte_off) {
+  return *reinterpret_cast<const u32*>(base + byte_off);
+}
 #else
 typedef u32 smem_addr_t;
 __device__ __forceinline__ smem_addr_t smem_addr(const void* p) {
@@ -151,6 +154,11 @@ __device__ __forceinline__ smem_addr_t smem_addr(const void* p) {
 __device__ __forceinline__ u32 lds_u16(smem_addr_t base, u32 byte_off) {
   u32 v;
   asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+  return v;
+}
+__device__ __forceinline__ u32 lds_u32(smem_addr_t base, u32 byte_off) {
+  u32 v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
   return v;
 }
 __device__ __forceinline__ uint2 lds_v2(smem_addr_t base, u32 byte_off) {

@@ -34,13 +34,33 @@ constexpr int kEncSubTileBytes = kEncThreads * kEncBytesPerThread;  // 4 KiB
 #define GH_ENC_SUBTILES 4
 #endif
 #ifndef GH_ENC_BLOCKS_PER_SM
-#define GH_ENC_BLOCKS_PER_SM 5
+#define GH_ENC_BLOCKS_PER_SM 4
 #endif
 constexpr int kEncSubTiles = GH_ENC_SUBTILES;
 constexpr int kEncTileBytes = kEncSubTileBytes * kEncSubTiles;      // 16 KiB per look-back
-// worst case per sub-tile: 4096 symbols x 32 bits + end mark 32, plus slack for the funnel shift
-constexpr int kEncStageWords = (kEncSubTileBytes * 32 + 32 + 31) / 32 + 2;
 constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
+
+// Shared memory of the encode kernel, per variant (kSymsPerChunk = 4: no code longer than 16 bits; 2: up to 32).
+//  * The (codeword, length) table is REPLICATED across the banks so that the per-byte gather is free of bank
+//    conflicts: with one copy, 32 lanes looking up 32 random bytes cost ~4 wavefronts per LDS and the L1 data
+//    pipe, not the ALUs, set the kernel's pace (profiles/r2b: 262 M shared-load wavefronts for 67 M lookups).
+//      variant 4: 32-bit entries  code | len << 16, one copy per lane: word (sym * 32 + lane)       -- 32 KiB,
+//                 every LDS is one wavefront whatever the data;
+//      variant 2: 64-bit entries (len << 32) | code, one copy per lane pair: slot (sym * 16 + lane % 16) -- 32 KiB,
+//                 lanes l and l + 16 share a slot (broadcast when their bytes are equal): at most 2-way.
+//  * staging: worst case per sub-tile = 4096 symbols x max code length (+ end mark, + slack for the funnel shift).
+template <int kSymsPerChunk>
+struct EncSmem {
+  static constexpr int kMaxLen = kSymsPerChunk == 4 ? 16 : 32;
+  static constexpr int kStageWords = (kEncSubTileBytes * kMaxLen + 32 + 31) / 32 + 2;
+  static constexpr int kLutWords = 256 * 32;
+  u32 lut[kLutWords];
+  u32 stage[2][kStageWords];
+  u32 warp_total[kEncSubTiles][kEncThreads / 32];
+  u32 carry[2];
+  u32 tile;
+  u64 tile_start;
+};
 
 constexpr u64 kFlagMask = 3ull << 62;
 constexpr u64 kFlagAggregate = 1ull << 62;  // value = bits of this tile only
@@ -80,27 +100,53 @@ __device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
   return (w >> (8 * (k & 3))) & 0xffu;
 }
 
+// gather from this lane's copy of the table (see EncSmem)
+template <int kSymsPerChunk>
+__device__ __forceinline__ u32 lut_len(smem_addr_t lut_lane, u32 byte) {
+  if (kSymsPerChunk == 4) return lds_u32(lut_lane, byte * 128u) >> 16;
+  return lds_u32(lut_lane, byte * 128u + 4u);
+}
+template <int kSymsPerChunk>
+__device__ __forceinline__ void lut_entry(smem_addr_t lut_lane, u32 byte, u32& code, u32& len) {
+  if (kSymsPerChunk == 4) {
+    const u32 e = lds_u32(lut_lane, byte * 128u);
+    code = e & 0xffffu;
+    len = e >> 16;
+  } else {
+    const uint2 e = lds_v2(lut_lane, byte * 128u);
+    code = e.x;
+    len = e.y;
+  }
+}
+
 template <int kSymsPerChunk>
 __global__ void __launch_bounds__(kEncThreads, kEncBlocksPerSm)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
               u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
   constexpr int kChunks = kEncBytesPerThread / kSymsPerChunk;
-  __shared__ u64 s_lut[GH_NSYM + 3];      // (len << 32) | code: one LDS.64 yields both
-  __shared__ uint8_t s_len[GH_NSYM + 3];  // lengths alone, for the counting pass
-  __shared__ u32 s_stage[2][kEncStageWords];
-  __shared__ u32 s_warp_total[kEncSubTiles][kEncThreads / 32];
-  __shared__ u32 s_carry[2];
-  __shared__ u32 s_tile;
-  __shared__ u64 s_tile_start;
+  typedef EncSmem<kSymsPerChunk> Smem;
+  GH_DYNAMIC_SMEM(smem_raw);
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  u32(&s_stage)[2][Smem::kStageWords] = sm.stage;
+  u32(&s_warp_total)[kEncSubTiles][kEncThreads / 32] = sm.warp_total;
+  u32(&s_carry)[2] = sm.carry;
+  u32& s_tile = sm.tile;
+  u64& s_tile_start = sm.tile_start;
 
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);
-  for (unsigned s = t; s < GH_NSYM; s += kEncThreads) {
-    s_lut[s] = (u64(table.length[s]) << 32) | table.codeword[s];
-    s_len[s] = table.length[s];
+  if (kSymsPerChunk == 4) {
+    for (unsigned i = t; i < 256u * 32u; i += kEncThreads) sm.lut[i] = table.codeword[i >> 5] | (u32(table.length[i >> 5]) << 16);
+  } else {
+    for (unsigned i = t; i < 256u * 16u; i += kEncThreads) {
+      sm.lut[2 * i] = table.codeword[i >> 4];
+      sm.lut[2 * i + 1] = table.length[i >> 4];
+    }
   }
-  for (unsigned i = t; i < 2u * kEncStageWords; i += kEncThreads) (&s_stage[0][0])[i] = 0;
+  for (unsigned i = t; i < 2u * Smem::kStageWords; i += kEncThreads) (&s_stage[0][0])[i] = 0;
   __syncthreads();
+  // this lane's copy of the table: entry of byte b at lut_lane + b * 128 (bytes)
+  const smem_addr_t lut_lane = smem_addr(sm.lut) + (kSymsPerChunk == 4 ? lane * 4u : (lane & 15u) * 8u);
   const u64 ntiles = enc_num_tiles(n);
   const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
   const u32 eof_len_all = table.length[GH_EOF_SYMBOL];
@@ -130,9 +176,9 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       u32 b = 0;
       if (cnt[j] == kEncBytesPerThread) {
 #pragma unroll
-        for (int k = 0; k < kEncBytesPerThread; ++k) b += s_len[vec_byte(raw[j], k)];
+        for (int k = 0; k < kEncBytesPerThread; ++k) b += lut_len<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
       } else {
-        for (int k = 0; k < cnt[j]; ++k) b += s_len[vec_byte(raw[j], k)];
+        for (int k = 0; k < cnt[j]; ++k) b += lut_len<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
       }
       const u64 base = tile * kEncTileBytes + u64(j) * kEncSubTileBytes + u64(t) * kEncBytesPerThread;
       if (append_eof && last_tile && base < n && base + kEncBytesPerThread >= n) {
@@ -210,9 +256,9 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
             u32 clen = 0;
 #pragma unroll
             for (int q = 0; q < kSymsPerChunk; ++q) {
-              const u64 e = s_lut[vec_byte(raw[j], c * kSymsPerChunk + q)];
-              const u32 len = u32(e >> 32);
-              acc = (acc << len) | u32(e);  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
+              u32 code, len;
+              lut_entry<kSymsPerChunk>(lut_lane, vec_byte(raw[j], c * kSymsPerChunk + q), code, len);
+              acc = (acc << len) | code;  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
               clen += len;
             }
             stage_bits(stage, pos, acc, clen);  // every byte value that occurs has a code: clen >= kSymsPerChunk
@@ -220,9 +266,10 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
           }
         } else {  // the ragged last vector of the input: symbol by symbol
           for (int k = 0; k < cnt[j]; ++k) {
-            const u64 e = s_lut[vec_byte(raw[j], k)];
-            stage_bits(stage, pos, u32(e), u32(e >> 32));
-            pos += u32(e >> 32);
+            u32 code, len;
+            lut_entry<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k), code, len);
+            stage_bits(stage, pos, code, len);
+            pos += len;
           }
         }
         if (end_sub == j && eof_len_all) stage_bits(stage, pos, eof_code, eof_len_all);
@@ -337,14 +384,28 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   const size_t used = size_t(p - static_cast<uint8_t*>(d_workspace)) + 8;
   GH_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, used, (cudaStream_t)stream));
 
+  static bool attrs_set = false;
+  if (!attrs_set) {  // both variants exceed the 48 KB a kernel gets without opting in
+    GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(EncSmem<4>))));
+    GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(EncSmem<2>))));
+    attrs_set = true;
+  }
   const u64 out_word_cap = payload_cap / 4;
-  u64 blocks = u64(sm_count() > 0 ? sm_count() : 1) * kEncBlocksPerSm;
+  // persistent blocks: as many as are resident at once (shared memory allows 4 of variant 4, 3 of variant 2)
+  const bool short_codes = code->max_len <= 16;
+  int per_sm = 0;
+#ifndef GH_EMUL
+  if (short_codes) GH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<4>, kEncThreads, sizeof(EncSmem<4>)));
+  else GH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<2>, kEncThreads, sizeof(EncSmem<2>)));
+#endif
+  if (per_sm < 1) per_sm = kEncBlocksPerSm;
+  u64 blocks = u64(sm_count() > 0 ? sm_count() : 1) * u64(per_sm);
   if (blocks > ntiles) blocks = ntiles;
-  if (code->max_len <= 16) {
-    GH_LAUNCH(encode_kernel<4>, unsigned(blocks), kEncThreads, 0, stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
+  if (short_codes) {
+    GH_LAUNCH(encode_kernel<4>, unsigned(blocks), kEncThreads, sizeof(EncSmem<4>), stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
               reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
   } else {
-    GH_LAUNCH(encode_kernel<2>, unsigned(blocks), kEncThreads, 0, stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
+    GH_LAUNCH(encode_kernel<2>, unsigned(blocks), kEncThreads, sizeof(EncSmem<2>), stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
               reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
   }
   rc = check_launch();

@@ -34,28 +34,32 @@ constexpr int kEncSubTileBytes = kEncThreads * kEncBytesPerThread;  // 4 KiB
 #define GH_ENC_SUBTILES 4
 #endif
 #ifndef GH_ENC_BLOCKS_PER_SM
-#define GH_ENC_BLOCKS_PER_SM 4
+#define GH_ENC_BLOCKS_PER_SM 5
 #endif
 constexpr int kEncSubTiles = GH_ENC_SUBTILES;
 constexpr int kEncTileBytes = kEncSubTileBytes * kEncSubTiles;      // 16 KiB per look-back
 constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
 
 // Shared memory of the encode kernel, per variant (kSymsPerChunk = 4: no code longer than 16 bits; 2: up to 32).
-//  * The (codeword, length) table is REPLICATED across the banks so that the per-byte gather is free of bank
-//    conflicts: with one copy, 32 lanes looking up 32 random bytes cost ~4 wavefronts per LDS and the L1 data
-//    pipe, not the ALUs, set the kernel's pace (profiles/r2b: 262 M shared-load wavefronts for 67 M lookups).
-//      variant 4: 32-bit entries  code | len << 16, one copy per lane: word (sym * 32 + lane)       -- 32 KiB,
-//                 every LDS is one wavefront whatever the data;
-//      variant 2: 64-bit entries (len << 32) | code, one copy per lane pair: slot (sym * 16 + lane % 16) -- 32 KiB,
-//                 lanes l and l + 16 share a slot (broadcast when their bytes are equal): at most 2-way.
+//  * The (codeword, length) table is REPLICATED across the banks so that the per-byte gather is (nearly) free of
+//    bank conflicts: with one copy, 32 lanes looking up 32 random bytes cost ~4 wavefronts per LDS and the L1 data
+//    pipe was as busy as the ALUs (profiles/r2b: 262 M shared-load wavefronts for 67 M lookups).
+//      variant 4: 32-bit entries  code << 16 | len, 16 copies: word (sym * 16 + lane % 16)             -- 16 KiB
+//      variant 2: 64-bit entries (len << 32) | code,  8 copies: slot (sym * 8 + lane % 8)              -- 16 KiB
+//    Lanes that share a copy are served by one broadcast when their bytes are equal, else serially.
 //  * staging: worst case per sub-tile = 4096 symbols x max code length (+ end mark, + slack for the funnel shift).
+//    Variant 4 rotates THREE staging buffers so that one barrier per sub-tile is enough (see the kernel).
 template <int kSymsPerChunk>
 struct EncSmem {
   static constexpr int kMaxLen = kSymsPerChunk == 4 ? 16 : 32;
   static constexpr int kStageWords = (kEncSubTileBytes * kMaxLen + 32 + 31) / 32 + 2;
-  static constexpr int kLutWords = 256 * 32;
+  static constexpr int kBuffers = kSymsPerChunk == 4 ? 3 : 2;
+  static constexpr int kCopies = kSymsPerChunk == 4 ? 16 : 8;
+  static constexpr int kEntryBytes = kSymsPerChunk == 4 ? 4 : 8;
+  static constexpr int kSymStride = kCopies * kEntryBytes;  // bytes between consecutive symbols' entries
+  static constexpr int kLutWords = 256 * kSymStride / 4;
   u32 lut[kLutWords];
-  u32 stage[2][kStageWords];
+  u32 stage[kBuffers][kStageWords];
   u32 warp_total[kEncSubTiles][kEncThreads / 32];
   u32 carry[2];
   u32 tile;
@@ -102,18 +106,19 @@ __device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
 
 // gather from this lane's copy of the table (see EncSmem)
 template <int kSymsPerChunk>
-__device__ __forceinline__ u32 lut_len(smem_addr_t lut_lane, u32 byte) {
-  if (kSymsPerChunk == 4) return lds_u32(lut_lane, byte * 128u) >> 16;
-  return lds_u32(lut_lane, byte * 128u + 4u);
+__device__ __forceinline__ u32 lut_word(smem_addr_t lut_lane, u32 byte) {  // variant 4: code << 16 | len; variant 2: len
+  typedef EncSmem<kSymsPerChunk> Smem;
+  return lds_u32(lut_lane, byte * u32(Smem::kSymStride) + (kSymsPerChunk == 4 ? 0u : 4u));
 }
 template <int kSymsPerChunk>
 __device__ __forceinline__ void lut_entry(smem_addr_t lut_lane, u32 byte, u32& code, u32& len) {
+  typedef EncSmem<kSymsPerChunk> Smem;
   if (kSymsPerChunk == 4) {
-    const u32 e = lds_u32(lut_lane, byte * 128u);
-    code = e & 0xffffu;
-    len = e >> 16;
+    const u32 e = lds_u32(lut_lane, byte * u32(Smem::kSymStride));
+    code = e >> 16;
+    len = e & 0xffffu;
   } else {
-    const uint2 e = lds_v2(lut_lane, byte * 128u);
+    const uint2 e = lds_v2(lut_lane, byte * u32(Smem::kSymStride));
     code = e.x;
     len = e.y;
   }
@@ -127,7 +132,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   typedef EncSmem<kSymsPerChunk> Smem;
   GH_DYNAMIC_SMEM(smem_raw);
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  u32(&s_stage)[2][Smem::kStageWords] = sm.stage;
+  u32(&s_stage)[Smem::kBuffers][Smem::kStageWords] = sm.stage;
   u32(&s_warp_total)[kEncSubTiles][kEncThreads / 32] = sm.warp_total;
   u32(&s_carry)[2] = sm.carry;
   u32& s_tile = sm.tile;
@@ -135,18 +140,21 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
 
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);
-  if (kSymsPerChunk == 4) {
-    for (unsigned i = t; i < 256u * 32u; i += kEncThreads) sm.lut[i] = table.codeword[i >> 5] | (u32(table.length[i >> 5]) << 16);
-  } else {
-    for (unsigned i = t; i < 256u * 16u; i += kEncThreads) {
-      sm.lut[2 * i] = table.codeword[i >> 4];
-      sm.lut[2 * i + 1] = table.length[i >> 4];
+  for (unsigned i = t; i < 256u * Smem::kCopies; i += kEncThreads) {
+    const unsigned sym = i / Smem::kCopies;
+    if (kSymsPerChunk == 4) {
+      sm.lut[i] = (table.codeword[sym] << 16) | table.length[sym];
+    } else {
+      sm.lut[2 * i] = table.codeword[sym];
+      sm.lut[2 * i + 1] = table.length[sym];
     }
   }
-  for (unsigned i = t; i < 2u * Smem::kStageWords; i += kEncThreads) (&s_stage[0][0])[i] = 0;
+  for (unsigned i = t; i < unsigned(Smem::kBuffers) * Smem::kStageWords; i += kEncThreads) (&s_stage[0][0])[i] = 0;
   __syncthreads();
-  // this lane's copy of the table: entry of byte b at lut_lane + b * 128 (bytes)
-  const smem_addr_t lut_lane = smem_addr(sm.lut) + (kSymsPerChunk == 4 ? lane * 4u : (lane & 15u) * 8u);
+  // this lane's copy of the table: entry of byte b at lut_lane + b * kSymStride
+  const smem_addr_t lut_lane = smem_addr(sm.lut) + (lane & u32(Smem::kCopies - 1)) * u32(Smem::kEntryBytes);
+  u32 buf = 0;        // staging buffer of the current sub-tile (rotates through kBuffers)
+  u32 prev_words = 0; // variant 4: words of the previous sub-tile's buffer that still have to be cleared
   const u64 ntiles = enc_num_tiles(n);
   const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
   const u32 eof_len_all = table.length[GH_EOF_SYMBOL];
@@ -174,12 +182,14 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
 #pragma unroll
     for (int j = 0; j < kEncSubTiles; ++j) {
       u32 b = 0;
+      // variant 4 sums whole entries: the lengths (<= 16 x 16) add up in the low half, the codes above them
       if (cnt[j] == kEncBytesPerThread) {
 #pragma unroll
-        for (int k = 0; k < kEncBytesPerThread; ++k) b += lut_len<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
+        for (int k = 0; k < kEncBytesPerThread; ++k) b += lut_word<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
       } else {
-        for (int k = 0; k < cnt[j]; ++k) b += lut_len<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
+        for (int k = 0; k < cnt[j]; ++k) b += lut_word<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
       }
+      if (kSymsPerChunk == 4) b &= 0xffffu;
       const u64 base = tile * kEncTileBytes + u64(j) * kEncSubTileBytes + u64(t) * kEncBytesPerThread;
       if (append_eof && last_tile && base < n && base + kEncBytesPerThread >= n) {
         end_sub = j;
@@ -246,7 +256,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
     u32 before = 0;  // bits of this tile in earlier sub-tiles
 #pragma unroll
     for (int j = 0; j < kEncSubTiles; ++j) {
-      u32* stage = s_stage[j & 1];
+      u32* stage = s_stage[buf];
       {
         u32 pos = pos0[j];
         if (cnt[j] == kEncBytesPerThread) {
@@ -254,12 +264,31 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
           for (int c = 0; c < kChunks; ++c) {
             u64 acc = 0;
             u32 clen = 0;
+            if (kSymsPerChunk == 4) {
+              // entries are code << 16 | len with len <= 16: the funnel shifts take the entry itself as distance
+              // (they use it modulo 32), and the lengths are summed as whole entries and masked once
+              u32 lo = 0, hi = 0, esum = 0;
 #pragma unroll
-            for (int q = 0; q < kSymsPerChunk; ++q) {
-              u32 code, len;
-              lut_entry<kSymsPerChunk>(lut_lane, vec_byte(raw[j], c * kSymsPerChunk + q), code, len);
-              acc = (acc << len) | code;  // len <= 16 (x4) or <= 32 (x2): at most 64 bits per chunk
-              clen += len;
+              for (int q = 0; q < 4; ++q) {
+                const u32 e = lut_word<4>(lut_lane, vec_byte(raw[j], c * 4 + q));
+                if (q == 0) {
+                  lo = e >> 16;
+                } else {
+                  hi = __funnelshift_l(lo, hi, e);
+                  lo = __funnelshift_l(0u, lo, e) | (e >> 16);
+                }
+                esum += e;
+              }
+              acc = (u64(hi) << 32) | lo;
+              clen = esum & 0xffffu;
+            } else {
+#pragma unroll
+              for (int q = 0; q < kSymsPerChunk; ++q) {
+                u32 code, len;
+                lut_entry<kSymsPerChunk>(lut_lane, vec_byte(raw[j], c * kSymsPerChunk + q), code, len);
+                acc = (acc << len) | code;  // len <= 32: at most 64 bits per chunk
+                clen += len;
+              }
             }
             stage_bits(stage, pos, acc, clen);  // every byte value that occurs has a code: clen >= kSymsPerChunk
             pos += clen;
@@ -299,8 +328,19 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
         else if (i == 0 && shared_head) ws.head[tile] = v;
         else if (gw < out_word_cap) out_words[gw] = be32(v);
       }
-      __syncthreads();  // (d_j) staged words consumed
-      for (u32 i = t; i < (nbits >> 5) + 3; i += kEncThreads) stage[i] = 0;  // clean for sub-tile j + 2
+      if (Smem::kBuffers == 3) {
+        // One barrier per sub-tile: the buffer of the PREVIOUS sub-tile is cleared now -- a thread passes barrier
+        // (c_j) only after it has finished reading that buffer -- and it is packed into again after barrier
+        // (c_j+1), which no thread passes before every thread has finished this clearing.
+        u32* prev = s_stage[buf == 0 ? 2 : buf - 1];
+        for (u32 i = t; i < prev_words; i += kEncThreads) prev[i] = 0;
+        prev_words = (nbits >> 5) + 3;
+        buf = buf == 2 ? 0 : buf + 1;
+      } else {
+        __syncthreads();  // (d_j) staged words consumed
+        for (u32 i = t; i < (nbits >> 5) + 3; i += kEncThreads) stage[i] = 0;  // clean for sub-tile j + 2
+        buf ^= 1;
+      }
       before += nbits;
     }
   }

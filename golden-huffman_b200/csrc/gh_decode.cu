@@ -35,10 +35,10 @@ namespace gh {
 
 constexpr int kDecThreads = 256;   // threads per block = subsequences per tile, all decode kernels
 #ifndef GH_DEC_S_BLOCKS
-#define GH_DEC_S_BLOCKS 5
+#define GH_DEC_S_BLOCKS 6
 #endif
 #ifndef GH_DEC_W_BLOCKS
-#define GH_DEC_W_BLOCKS 1
+#define GH_DEC_W_BLOCKS 4
 #endif
 constexpr u32 kNoEof = 0xffffffffu;
 constexpr u32 kEofPosUnknown = 0xfffffffeu;
@@ -294,6 +294,7 @@ constexpr u32 kCurBusy = 0x1E0u;     // any of these bits set: no lookup now
 constexpr u32 kCurMissBit = 0x200u;  // ... and this one set as well: the last lookup missed
 constexpr u32 kCurFieldMask = 0x3ffu;
 constexpr int kUnitWords = 8;        // a lane's reads are 32-byte units
+constexpr int kLutMaxBits = kLutCBits > kLutWBits ? (kLutCBits > 12 ? kLutCBits : 12) : (kLutWBits > 12 ? kLutWBits : 12);  // builder grid: one thread per entry of the largest table
 
 template <int K, int SC>  // K index bits, entries of (1 << SC) bytes
 struct CursorGeom {
@@ -1266,7 +1267,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     int rc = build_decode_tables(code, &tables);
     if (rc != GH_OK) return rc;
     GH_CUDA_TRY(cudaMemcpyAsync(const_cast<DecodeTables*>(ws.tables), &tables, sizeof(tables), cudaMemcpyHostToDevice, stream));
-    GH_LAUNCH(dec_build_luts_kernel, (1u << kLutCBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
+    GH_LAUNCH(dec_build_luts_kernel, (1u << kLutMaxBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
               const_cast<uint16_t*>(ws.lutC), const_cast<uint2*>(ws.lutW), const_cast<u32*>(ws.lutP));
     const bool slow_code = code->max_len - code->min_len <= 1;
     // measured (profiles/r1i): the fine pipeline is not yet faster than the coarse one, so it is opt-in

@@ -39,13 +39,21 @@ constexpr int kEncSubTileBytes = kEncThreads * kEncBytesPerThread;  // 4 KiB
 constexpr int kEncSubTiles = GH_ENC_SUBTILES;
 constexpr int kEncTileBytes = kEncSubTileBytes * kEncSubTiles;      // 16 KiB per look-back
 constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
+#ifndef GH_ENC_LOOK_DEPTH
+#define GH_ENC_LOOK_DEPTH 1
+#endif
+#ifndef GH_ENC_TICKET_SUBTILE
+#define GH_ENC_TICKET_SUBTILE 2
+#endif
+constexpr int kEncLookDepth = GH_ENC_LOOK_DEPTH;        // look-back rounds whose loads are in flight together
+constexpr int kEncTicketSubTile = GH_ENC_TICKET_SUBTILE;  // sub-tile during which the block draws its next tile
 
 // Shared memory of the encode kernel, per variant (kSymsPerChunk = 4: no code longer than 16 bits; 2: up to 32).
 //  * The (codeword, length) table is REPLICATED across the banks so that the per-byte gather is (nearly) free of
 //    bank conflicts: with one copy, 32 lanes looking up 32 random bytes cost ~4 wavefronts per LDS and the L1 data
 //    pipe was as busy as the ALUs (profiles/r2b: 262 M shared-load wavefronts for 67 M lookups).
 //      variant 4: 32-bit entries  code << 16 | len, 16 copies: word (sym * 16 + lane % 16)             -- 16 KiB
-//      variant 2: 64-bit entries (len << 32) | code,  8 copies: slot (sym * 8 + lane % 8)              -- 16 KiB
+//      variant 2: 64-bit entries (len << 32) | code,  4 copies: slot (sym * 4 + lane % 4)              --  8 KiB
 //    Lanes that share a copy are served by one broadcast when their bytes are equal, else serially.
 //  * staging: worst case per sub-tile = 4096 symbols x max code length (+ end mark, + slack for the funnel shift).
 //    Variant 4 rotates THREE staging buffers so that one barrier per sub-tile is enough (see the kernel).
@@ -54,7 +62,7 @@ struct EncSmem {
   static constexpr int kMaxLen = kSymsPerChunk == 4 ? 16 : 32;
   static constexpr int kStageWords = (kEncSubTileBytes * kMaxLen + 32 + 31) / 32 + 2;
   static constexpr int kBuffers = kSymsPerChunk == 4 ? 3 : 2;
-  static constexpr int kCopies = kSymsPerChunk == 4 ? 16 : 8;
+  static constexpr int kCopies = kSymsPerChunk == 4 ? 16 : 4;
   static constexpr int kEntryBytes = kSymsPerChunk == 4 ? 4 : 8;
   static constexpr int kSymStride = kCopies * kEntryBytes;  // bytes between consecutive symbols' entries
   static constexpr int kLutWords = 256 * kSymStride / 4;
@@ -231,21 +239,28 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
         if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
         exclusive = 0;
         long long look = (long long)tile - 1;
-        while (true) {
-          const long long idx = look - (long long)lane;
-          u64 st = kFlagPrefix;  // virtual tiles before tile 0 contribute nothing
-          if (idx >= 0) {
-            do {
-              st = ld_volatile_u64(ws.tile_state + idx);
-            } while ((st & kFlagMask) == 0);
+        bool done = false;
+        while (!done) {
+          // kEncLookDepth x 32 predecessors per L2 round trip: all loads are issued before the first is examined
+          u64 st[kEncLookDepth];
+#pragma unroll
+          for (int r = 0; r < kEncLookDepth; ++r) {
+            const long long idx = look - (long long)lane - 32 * r;
+            st[r] = idx >= 0 ? ld_volatile_u64(ws.tile_state + idx) : kFlagPrefix;  // virtual tiles before tile 0 add nothing
           }
-          const unsigned has_prefix = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
-          // lanes up to and including the nearest tile that already knows its prefix contribute
-          const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
-          const u64 contrib = (has_prefix == 0 || lane <= first) ? (st & ~kFlagMask) : 0ull;
-          exclusive += warp_sum64(contrib);
-          if (has_prefix) break;
-          look -= 32;
+#pragma unroll
+          for (int r = 0; r < kEncLookDepth; ++r) {
+            if (done) break;
+            const long long idx = look - (long long)lane - 32 * r;
+            while ((st[r] & kFlagMask) == 0) st[r] = ld_volatile_u64(ws.tile_state + idx);  // not published yet
+            const unsigned has_prefix = __ballot_sync(0xffffffffu, (st[r] & kFlagMask) == kFlagPrefix);
+            // lanes up to and including the nearest tile that already knows its prefix contribute
+            const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
+            const u64 contrib = (has_prefix == 0 || lane <= first) ? (st[r] & ~kFlagMask) : 0ull;
+            exclusive += warp_sum64(contrib);
+            done = has_prefix != 0;
+          }
+          look -= 32 * kEncLookDepth;
         }
         if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
       }
@@ -304,7 +319,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
         if (end_sub == j && eof_len_all) stage_bits(stage, pos, eof_code, eof_len_all);
       }
       __syncthreads();  // (c_j) staging of sub-tile j complete; for j == 0 also: s_tile_start written
-      if (j == 0 && t == 0) s_tile = atomicAdd(ws.ticket, 1u);  // next tile (read after the last barrier below)
+      if (j == kEncTicketSubTile && t == 0) s_tile = atomicAdd(ws.ticket, 1u);  // next tile (read after a later barrier)
 
       const u64 G = s_tile_start + before;  // global bit offset of this sub-tile
       const u32 nbits = sub_bits[j];

@@ -15,10 +15,10 @@ namespace gh {
 //   lut1  2^12 x u16   one codeword per lookup: (symbol << 6) | length, 0 = codeword longer than 12 bits.
 //                      The device analogue of TableCanonicalHuffDecoder::lookup_table_
 //                      (reference include/canonical_huff_encoder.cc:466-516) with the symbol folded in.
-//   lutC  2^14 x u16   as many whole codewords as fit in 14 bits (never the end mark), as ONE addend for the
+//   lutC  2^13 x u16   as many whole codewords as fit in 13 bits (never the end mark), as ONE addend for the
 //                      decoder's cursor word:  (codewords << 10) - total length.  kLutMiss = the first codeword does
 //                      not fit or is the end mark. Used where only counts matter.
-//   lutW  2^13 x u32x2 up to 4 whole codewords in 13 bits: .x = (8 * codewords << 10) - total length (one addend that
+//   lutW  2^11 x u32x2 up to 4 whole codewords in 11 bits: .x = (8 * codewords << 10) - total length (one addend that
 //                      advances the output fill in bits and moves the cursor), .y = the symbols, first in the lowest
 //                      byte. .x = kLutMiss when the first codeword does not fit or is the end mark.
 //   lutP  2^12 x u32   one or two whole codewords in 12 bits, with the first length kept so a step can stop after
@@ -27,10 +27,10 @@ namespace gh {
 constexpr int kLut1Bits = 12;
 constexpr int kLutPBits = 12;
 #ifndef GH_LUTC_BITS
-#define GH_LUTC_BITS 14
+#define GH_LUTC_BITS 13
 #endif
 #ifndef GH_LUTW_BITS
-#define GH_LUTW_BITS 13
+#define GH_LUTW_BITS 11
 #endif
 constexpr int kLutCBits = GH_LUTC_BITS;
 constexpr int kLutWBits = GH_LUTW_BITS;

@@ -71,6 +71,7 @@ struct DecControl {  // device-resident, copied back to the host after each roun
   u64 n_sub;
   u32 eof_prefix;     // symbols before the first end mark inside subsequence eof_index
   u32 fine;           // 1: fine-grained pipeline (2 KiB segments, piece states valid)
+  u32 work_count;     // entries appended to the next re-walk list in this round
 };
 
 struct DecWorkspace {
@@ -85,6 +86,7 @@ struct DecWorkspace {
   u32* eofpos;     // [n_sub]  symbols before the path's first end mark, kEofPosUnknown if it was not observed
   u64* out_off;    // [n_sub]  output offset of each subsequence's first symbol
   u32* pieces;     // [32 * n_sub] fine pipeline only: state of each 64-byte piece
+  u32* work[2];    // [n_sub] each: subsequences to re-walk in this / the next round (near-fixed-length codes)
   u64* tile_sum;   // [n_tiles]
   u64* tile_base;  // [n_tiles]
 };
@@ -357,13 +359,11 @@ __device__ __forceinline__ void load_speculate_tables(SmemSpeculate& s, const De
     reinterpret_cast<uint4*>(s.lutC)[i] = reinterpret_cast<const uint4*>(ws.lutC)[i];
 }
 
-__global__ void __launch_bounds__(kDecThreads, GH_DEC_S_BLOCKS)
-dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
-  __shared__ SmemSpeculate s;
-  load_speculate_tables(s, ws);
-  __syncthreads();
-  const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
-  if (i >= g.n_sub) return;
+// Walks subsequence i from its entry (first pass: bit 0, or the true entry for subsequence 0; re-walk: the left
+// neighbour's current exit) and stores its state. Returns whether a re-walk moved the exit.
+__device__ __forceinline__ bool speculate_subsequence(SmemSpeculate& s, const DecGeometry& g, const DecWorkspace& ws, u64 i,
+                                                      int respeculate) {
+
   const u64 start = i * u64(g.sub_bytes) * 8;
   const u32 end = u32(sub_end_bits(g, i));
   u32 entry = (i == 0) ? g.entry0 : 0u;
@@ -374,7 +374,7 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
     // corrected path once with this kernel's bulk loop is several times cheaper. Same fixed-point iteration.
     const u64 mine = ld_volatile_u64(ws.sub + i);
     if (i > 0) entry = st_exit(ld_volatile_u64(ws.sub + i - 1));
-    if (entry == st_entry(mine)) return;
+    if (entry == st_entry(mine)) return false;
     old_exit = st_exit(mine);
   }
   u32 pos = entry, count = 0, neof = 0, first_eof = kNoEof;
@@ -467,9 +467,57 @@ dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate) {
   ws.neof[i] = neof;
   ws.eofpos[i] = first_eof;  // codewords before the first end mark are all symbols
   st_volatile_u64(ws.sub + i, pack_state(count, entry, pos - end, neof != 0));
-  if (respeculate && (pos - end) != old_exit) {
-    ws.ctl->changed = 1u;
-    atomicAdd(&ws.ctl->exits_changed, 1u);
+  return respeculate && (pos - end) != old_exit;
+}
+
+
+
+__global__ void __launch_bounds__(kDecThreads, GH_DEC_S_BLOCKS)
+dec_speculate_kernel(DecGeometry g, DecWorkspace ws, int respeculate, const u32* __restrict__ work_in, u32 work_n,
+                     u32* __restrict__ work_out) {
+  __shared__ SmemSpeculate s;
+  load_speculate_tables(s, ws);
+  __syncthreads();
+  // first pass: thread = subsequence. Re-walk rounds: thread = entry of the dense list of subsequences whose left
+  // neighbour's exit moved in the previous round (so the warps of a round are full whatever fraction is stale).
+  const u64 slot = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  const bool live = respeculate ? slot < u64(work_n) : slot < g.n_sub;
+  const u64 i = live ? (respeculate ? u64(work_in[slot]) : slot) : 0;
+  bool moved = false;
+  if (live) moved = speculate_subsequence(s, g, ws, i, respeculate);
+  if (!respeculate) return;
+  // append i + 1 to the next round's list (one atomic per warp)
+  const bool push = moved && i + 1 < g.n_sub;
+  const unsigned mask = __ballot_sync(0xffffffffu, push);
+  if (mask) {
+    const unsigned lane = threadIdx.x & 31;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(&ws.ctl->work_count, u32(__popc(mask)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (push) work_out[base + __popc(mask & ((1u << lane) - 1u))] = u32(i + 1);
+    if (lane == 0) {
+      ws.ctl->changed = 1u;
+      atomicAdd(&ws.ctl->exits_changed, u32(__popc(mask)));
+    }
+  }
+}
+
+// first list of a re-walk phase: every subsequence whose assumed entry is not its left neighbour's exit
+__global__ void __launch_bounds__(kDecThreads)
+dec_worklist_kernel(DecGeometry g, DecWorkspace ws, u32* __restrict__ work_out) {
+  const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  bool push = false;
+  if (i < g.n_sub) {
+    const u32 want = (i == 0) ? g.entry0 : st_exit(ws.sub[i - 1]);
+    push = want != st_entry(ws.sub[i]);
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, push);
+  if (mask) {
+    const unsigned lane = threadIdx.x & 31;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(&ws.ctl->work_count, u32(__popc(mask)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (push) work_out[base + __popc(mask & ((1u << lane) - 1u))] = u32(i);
   }
 }
 
@@ -1178,7 +1226,7 @@ static int set_fine_attrs() {  // opt-in to > 48 KB of dynamic shared memory for
 }
 
 struct DecLayout {
-  size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_pieces, off_tile_sum, off_tile_base, total;
+  size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_pieces, off_work0, off_work1, off_tile_sum, off_tile_base, total;
 };
 
 static DecLayout dec_layout(u64 slice_bytes) {
@@ -1197,7 +1245,9 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_eofpos = L.off_neof + up(size_t(max_sub) * 4);
   L.off_out_off = L.off_eofpos + up(size_t(max_sub) * 4);
   L.off_pieces = L.off_out_off + up(size_t(max_sub) * 8);
-  L.off_tile_sum = L.off_pieces + up((size_t(slice_bytes) / kFineSubBytes + 2) * 32 * 4);
+  L.off_work0 = L.off_pieces + up((size_t(slice_bytes) / kFineSubBytes + 2) * 32 * 4);
+  L.off_work1 = L.off_work0 + up(size_t(max_sub) * 4);
+  L.off_tile_sum = L.off_work1 + up(size_t(max_sub) * 4);
   L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
   L.total = L.off_tile_base + up(size_t(max_tiles) * 8);
   return L;
@@ -1217,6 +1267,8 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   w.eofpos = reinterpret_cast<u32*>(p + L.off_eofpos);
   w.out_off = reinterpret_cast<u64*>(p + L.off_out_off);
   w.pieces = reinterpret_cast<u32*>(p + L.off_pieces);
+  w.work[0] = reinterpret_cast<u32*>(p + L.off_work0);
+  w.work[1] = reinterpret_cast<u32*>(p + L.off_work1);
   w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
   w.tile_base = reinterpret_cast<u64*>(p + L.off_tile_base);
   return w;
@@ -1305,25 +1357,60 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
         GH_LAUNCH(dec_fine_speculate_kernel, unsigned((g.n_sub + kFineWarps - 1) / kFineWarps), kFineWarps * 32,
                   sizeof(SmemFineSpec), stream, g, ws);
       } else {
-        GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws, 0);
+        GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws, 0, (const u32*)nullptr, 0u, (u32*)nullptr);
       }
       int rc = check_launch();
       if (rc != GH_OK) return rc;
     }
     bool coarsen = false;
-    for (u32 level_round = 0;; ++level_round) {
+    bool have_list = false;  // re-walk rounds: work[cur] lists the subsequences to walk, work_n of them
+    u32 cur = 0, work_n = 0;
+    auto reset_ctl = [&]() -> int {
       h_ctl = DecControl();
       h_ctl.eof_index = kNoEof;
       h_ctl.sub_bytes = g.sub_bytes;
       h_ctl.n_sub = g.n_sub;
       h_ctl.fine = fine ? 1u : 0u;
       GH_CUDA_TRY(cudaMemcpyAsync(ws.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, stream));
-      if (rewalk && !fine) GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws, 1);
-      else GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
-      int rc = check_launch();
-      if (rc != GH_OK) return rc;
+      return GH_OK;
+    };
+    auto read_ctl = [&]() -> int {
       GH_CUDA_TRY(cudaMemcpyAsync(&h_ctl, ws.ctl, sizeof(h_ctl), cudaMemcpyDeviceToHost, stream));
       GH_CUDA_TRY(cudaStreamSynchronize(stream));
+      return GH_OK;
+    };
+    for (u32 level_round = 0;; ++level_round) {
+      int rc = reset_ctl();
+      if (rc != GH_OK) return rc;
+      if (rewalk && !fine) {
+        // Re-walk rounds run over a dense list of the stale subsequences: a round costs what it re-walks, not a
+        // pass over every subsequence with mostly idle lanes (uniform bytes: ten rounds, the later ones tiny).
+        if (!have_list) {
+          GH_LAUNCH(dec_worklist_kernel, blocks, kDecThreads, 0, stream, g, ws, ws.work[cur]);
+          rc = check_launch();
+          if (rc == GH_OK) rc = read_ctl();
+          if (rc != GH_OK) return rc;
+          work_n = h_ctl.work_count;
+          have_list = true;
+          rc = reset_ctl();
+          if (rc != GH_OK) return rc;
+        }
+        if (work_n) {
+          GH_LAUNCH(dec_speculate_kernel, (work_n + kDecThreads - 1) / kDecThreads, kDecThreads, 0, stream, g, ws, 1,
+                    (const u32*)ws.work[cur], work_n, ws.work[cur ^ 1]);
+        }
+      } else {
+        GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
+        have_list = false;
+      }
+      rc = check_launch();
+      if (rc != GH_OK) return rc;
+      rc = read_ctl();
+      if (rc != GH_OK) return rc;
+      if (rewalk && !fine) {
+        cur ^= 1;
+        work_n = h_ctl.work_count;
+      }
       ++rounds;
       if (!h_ctl.changed) break;
       // more than a tenth of the exits moved: the paths do not meet early with this code, stop trying to

@@ -52,6 +52,14 @@ def test_emulated_kernels_on_golden(emu, ctx, oracle, name):
     _roundtrip(emu, ctx, oracle, make_input(name))
 
 
+def test_emulated_near_fixed_length_code(emu, ctx, oracle):
+    """every byte value equally often -> 255 codes of 8 bits + 2 of 9: paths re-synchronise only after thousands of
+    symbols, so the decoder takes its re-walk rounds over dense work lists (and coarsens the subsequences)"""
+    _roundtrip(emu, ctx, oracle, make_input("kat3_allbytes512"))
+    rng = np.random.default_rng(11)
+    _roundtrip(emu, ctx, oracle, rng.permutation(np.repeat(np.arange(256, dtype=np.uint8), 300)).tobytes())
+
+
 def test_emulated_kernels_random(emu, ctx, oracle):
     rng = np.random.default_rng(3)
     sizes = [3, 17, 4095, 8193, 30000]

@@ -33,6 +33,21 @@
 
 namespace gh {
 
+// lutW entry: 64 bits (addend, 4 symbols) or, with GH_LUTW_U32, 32 bits (addend << 16 | 2 symbols): half the
+// shared-memory wavefronts per lookup for slightly fewer symbols per lookup
+#ifndef GH_LUTW_U64
+#define GH_LUTW_U32 1
+#endif
+#ifdef GH_LUTW_U32
+typedef uint32_t LutWEntry;
+constexpr int kLutWEntryShift = 2;
+constexpr int kLutWSyms = 2;
+#else
+typedef uint2 LutWEntry;
+constexpr int kLutWEntryShift = 3;
+constexpr int kLutWSyms = kLutWMaxSyms;
+#endif
+
 constexpr int kDecThreads = 256;   // threads per block = subsequences per tile, all decode kernels
 #ifndef GH_DEC_S_BLOCKS
 #define GH_DEC_S_BLOCKS 6
@@ -78,7 +93,7 @@ struct DecWorkspace {
   const DecodeTables* tables;  // small canonical tables (host-built)
   const uint16_t* lut1;        // [2^12]  device-built, see gh_internal.h
   const uint16_t* lutC;        // [2^kLutCBits]
-  const uint2* lutW;           // [2^kLutWBits]
+  const LutWEntry* lutW;       // [2^kLutWBits]
   const u32* lutP;             // [2^12]
   DecControl* ctl;
   u64* sub;        // [n_sub]
@@ -150,7 +165,7 @@ __device__ __noinline__ u32 decode_one_packed(const SmemCanon* s, const uint16_t
 // thread w handles window value w of each table it is in range for
 __global__ void __launch_bounds__(256)
 dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restrict__ lut1, uint16_t* __restrict__ lutC,
-                      uint2* __restrict__ lutW, u32* __restrict__ lutP) {
+                      LutWEntry* __restrict__ lutW, u32* __restrict__ lutP) {
   __shared__ SmemCanon s;
   load_canon(s, tables);
   __syncthreads();
@@ -179,8 +194,12 @@ dec_build_luts_kernel(const DecodeTables* __restrict__ tables, uint16_t* __restr
     lutC[w] = uint16_t(ns ? ((ns << kCurShift) - tl) : kLutMiss);
   }
   if (w < (1u << kLutWBits)) {
-    walk(w, kLutWBits, kLutWMaxSyms, tl, ns, pk);
+    walk(w, kLutWBits, kLutWSyms, tl, ns, pk);
+#ifdef GH_LUTW_U32
+    lutW[w] = ns ? ((((ns << (kCurShift + 3)) - tl) << 16) | pk) : (kLutMiss << 16);
+#else
     lutW[w] = ns ? make_uint2((ns << (kCurShift + 3)) - tl, pk) : make_uint2(kLutMiss, 0u);
+#endif
   }
   if (w < (1u << kLutPBits)) {
     walk(w, kLutPBits, 2, tl, ns, pk);
@@ -332,9 +351,17 @@ __device__ __forceinline__ u64 cursor_position(u64 ulast, u32 acc) {
 
 // the 32 stream bits at the cursor of a lane whose last lookup missed (F already reduced by kLutMiss)
 template <int K, int SC>
-__device__ __forceinline__ u32 cursor_window32(u32 hi, u32 lo, u32 next_raw, u32 acc) {
+__device__ __forceinline__ u32 cursor_window32(u32 hi, u32 lo, u32 next_be, u32 acc) {
   const u32 c = u32(CursorGeom<K, SC>::S0 + int(kCurBase) - int(acc & kCurFieldMask));  // CMIN .. S0
-  return c < 32u ? __funnelshift_l(lo, hi, c) : __funnelshift_l(be32(next_raw), lo, c - 32u);
+  return c < 32u ? __funnelshift_l(lo, hi, c) : __funnelshift_l(next_be, lo, c - 32u);
+}
+
+// All eight words of a unit to stream order at once, BEFORE the next unit's load is issued: ptxas may give both
+// loads the same scoreboard, and then the first read of a unit's registers issued after the next load would wait
+// for that load as well -- a full memory latency per unit (profiles/r2h: 12 % of the writer's stall samples).
+__device__ __forceinline__ void unit_to_stream_order(Unit8& u) {
+#pragma unroll
+  for (int k = 0; k < kUnitWords; ++k) u.w[k] = be32(u.w[k]);
 }
 
 __device__ __forceinline__ bool lutc_hit(u32 e, u32& len, u32& cnt) {  // for the walks outside the bulk loops
@@ -391,12 +418,11 @@ __device__ __forceinline__ bool speculate_subsequence(SmemSpeculate& s, const De
       const smem_addr_t lut = smem_addr(s.lutC);
       u32 hi, lo = 0;
       // one 32-byte unit: eight word steps
-      auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {
+      auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {  // cu in stream order, the next unit's word raw
 #pragma unroll
         for (int k = 0; k < kUnitWords; ++k) {
-          const u32 next_raw = k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : next_unit_word0;
           hi = lo;
-          lo = be32(cu.w[k]);
+          lo = cu.w[k];
           acc += 32u;
           while ((acc & kCurBusy) == 0u) {
             do {
@@ -406,7 +432,8 @@ __device__ __forceinline__ bool speculate_subsequence(SmemSpeculate& s, const De
             if ((acc & kCurMissBit) == 0u) break;
             // first codeword longer than the table window, or the end mark
             acc -= kLutMiss;
-            const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutCBits, 1>(hi, lo, next_raw, acc));
+            const u32 next_be = k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : be32(next_unit_word0);
+            const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutCBits, 1>(hi, lo, next_be, acc));
             if ((sl >> 8) == u32(GH_EOF_SYMBOL)) {
               if (!neof) first_eof = count + (acc >> kCurShift);
               ++neof;
@@ -420,10 +447,12 @@ __device__ __forceinline__ bool speculate_subsequence(SmemSpeculate& s, const De
       // two unit buffers that swap roles, so the unit in flight is never copied (a copy would wait for the load)
       Unit8 ua = ldg_unit(g.payload + 32 * u, aligned32), ub;
       while (true) {
+        unit_to_stream_order(ua);
         ub = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
         walk_unit(ua, ub.w[0]);
         if (u == ulast) break;
         ++u;
+        unit_to_stream_order(ub);
         ua = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
         walk_unit(ub, ua.w[0]);
         if (u == ulast) break;
@@ -741,7 +770,7 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
 struct SmemWrite {
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
-  uint2 lutW[1 << kLutWBits];
+  LutWEntry lutW[1 << kLutWBits];
   u32 warp_total[kDecThreads / 32];
 };
 
@@ -806,7 +835,7 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   load_canon(s.canon, ws.tables);
   for (unsigned i = threadIdx.x; i < (1u << kLut1Bits) / 8; i += kDecThreads)
     reinterpret_cast<uint4*>(s.lut1)[i] = reinterpret_cast<const uint4*>(ws.lut1)[i];
-  for (unsigned i = threadIdx.x; i < (1u << kLutWBits) / 2; i += kDecThreads)
+  for (unsigned i = threadIdx.x; i < (sizeof(LutWEntry) << kLutWBits) / 16; i += kDecThreads)
     reinterpret_cast<uint4*>(s.lutW)[i] = reinterpret_cast<const uint4*>(ws.lutW)[i];
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const u64 i = u64(blockIdx.x) * kDecThreads + t;
@@ -850,11 +879,11 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   // bulk: every codeword that starts before `end` belongs to this lane (that is what `count` counted), so the loop
   // is bounded by the bit position alone; a lane whose output was clipped by out_cap takes the slow path only.
   {
-    typedef CursorGeom<kLutWBits, 3> G;
+    typedef CursorGeom<kLutWBits, kLutWEntryShift> G;
     u64 u, ulast;
     u32 acc;
     if (remaining && u64(count) <= out_cap - o && pos < end &&
-        cursor_plan<kLutWBits, 3>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
+        cursor_plan<kLutWBits, kLutWEntryShift>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
       const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
       const u64 umax = (g.readable >> 5) - 1;
       const smem_addr_t lut = smem_addr(s.lutW);
@@ -876,23 +905,28 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         queue_push_store(q0, q1, q2, q3, part, merged, spill, flipped & (32u << kCurShift),
                          flipped & (128u << kCurShift), glo, ghi, one);
       };
-      auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {
+      auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {  // cu in stream order, the next unit's word raw
 #pragma unroll
         for (int k = 0; k < kUnitWords; ++k) {
-          const u32 next_raw = k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : next_unit_word0;
           hi = lo;
-          lo = be32(cu.w[k]);
+          lo = cu.w[k];
           acc += 32u;
           while ((acc & kCurBusy) == 0u) {
             do {
               const u32 x = __funnelshift_r(lo, hi, acc);
+#ifdef GH_LUTW_U32
+              const u32 e = lds_u32(lut, x & G::kMask);
+              append(__umulhi(e, 1u << 16), e & 0xffffu);
+#else
               const uint2 e = lds_v2(lut, x & G::kMask);
               append(e.x, e.y);
+#endif
             } while ((acc & kCurBusy) == 0u);
             if ((acc & kCurMissBit) == 0u) break;
             // codeword longer than the table window, or the end mark (only in the subsequence that ends the stream)
             acc -= kLutMiss;
-            const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutWBits, 3>(hi, lo, next_raw, acc));
+            const u32 next_be = k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : be32(next_unit_word0);
+            const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutWBits, kLutWEntryShift>(hi, lo, next_be, acc));
             if ((sl >> 8) == u32(GH_EOF_SYMBOL)) {
               stop = true;
               acc = (acc & ~kCurFieldMask) | 192u;  // stays below the allowed range for the rest of this unit
@@ -905,10 +939,12 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
       // two unit buffers that swap roles, so the unit in flight is never copied (a copy would wait for the load)
       Unit8 ua = ldg_unit(g.payload + 32 * u, aligned32), ub;
       while (true) {
+        unit_to_stream_order(ua);
         ub = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
         walk_unit(ua, ub.w[0]);
         if (stop || u == ulast) break;
         ++u;
+        unit_to_stream_order(ub);
         ua = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
         walk_unit(ub, ua.w[0]);
         if (stop || u == ulast) break;
@@ -924,7 +960,7 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
       const u64 emitted = u64(gdst - dst) + (open_bits >> 3);
       dst += emitted;
       remaining = stop ? 0u : remaining - u32(emitted);
-      pos = u32(cursor_position<kLutWBits, 3>(ulast, acc) - start);
+      pos = u32(cursor_position<kLutWBits, kLutWEntryShift>(ulast, acc) - start);
     }
   }
   // what the bulk loop left (the last few bits of the subsequence, the payload tail, clipped output): one codeword
@@ -1238,7 +1274,7 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_lut1 = up(sizeof(DecodeTables));
   L.off_lutC = L.off_lut1 + up(sizeof(uint16_t) << kLut1Bits);
   L.off_lutW = L.off_lutC + up(sizeof(uint16_t) << kLutCBits);
-  L.off_lutP = L.off_lutW + up(sizeof(uint2) << kLutWBits);
+  L.off_lutP = L.off_lutW + up(sizeof(LutWEntry) << kLutWBits);
   L.off_ctl = L.off_lutP + up(sizeof(u32) << kLutPBits);
   L.off_sub = L.off_ctl + 256;
   L.off_neof = L.off_sub + up(size_t(max_sub) * 8);
@@ -1259,7 +1295,7 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   w.tables = reinterpret_cast<const DecodeTables*>(p + L.off_tables);
   w.lut1 = reinterpret_cast<const uint16_t*>(p + L.off_lut1);
   w.lutC = reinterpret_cast<const uint16_t*>(p + L.off_lutC);
-  w.lutW = reinterpret_cast<const uint2*>(p + L.off_lutW);
+  w.lutW = reinterpret_cast<const LutWEntry*>(p + L.off_lutW);
   w.lutP = reinterpret_cast<const u32*>(p + L.off_lutP);
   w.ctl = reinterpret_cast<DecControl*>(p + L.off_ctl);
   w.sub = reinterpret_cast<u64*>(p + L.off_sub);
@@ -1320,7 +1356,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     if (rc != GH_OK) return rc;
     GH_CUDA_TRY(cudaMemcpyAsync(const_cast<DecodeTables*>(ws.tables), &tables, sizeof(tables), cudaMemcpyHostToDevice, stream));
     GH_LAUNCH(dec_build_luts_kernel, (1u << kLutMaxBits) / 256, 256, 0, stream, ws.tables, const_cast<uint16_t*>(ws.lut1),
-              const_cast<uint16_t*>(ws.lutC), const_cast<uint2*>(ws.lutW), const_cast<u32*>(ws.lutP));
+              const_cast<uint16_t*>(ws.lutC), const_cast<LutWEntry*>(ws.lutW), const_cast<u32*>(ws.lutP));
     const bool slow_code = code->max_len - code->min_len <= 1;
     // measured (profiles/r1i): the fine pipeline is not yet faster than the coarse one, so it is opt-in
     fine = pipeline_choice() == 2;

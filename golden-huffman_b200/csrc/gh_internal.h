@@ -30,7 +30,7 @@ constexpr int kLutPBits = 12;
 #define GH_LUTC_BITS 13
 #endif
 #ifndef GH_LUTW_BITS
-#define GH_LUTW_BITS 11
+#define GH_LUTW_BITS 12
 #endif
 constexpr int kLutCBits = GH_LUTC_BITS;
 constexpr int kLutWBits = GH_LUTW_BITS;

@@ -422,7 +422,7 @@ __device__ __forceinline__ bool speculate_subsequence(SmemSpeculate& s, const De
 #pragma unroll
         for (int k = 0; k < kUnitWords; ++k) {
           hi = lo;
-          lo = cu.w[k];
+          lo = be32(cu.w[k]);
           acc += 32u;
           while ((acc & kCurBusy) == 0u) {
             do {
@@ -432,7 +432,7 @@ __device__ __forceinline__ bool speculate_subsequence(SmemSpeculate& s, const De
             if ((acc & kCurMissBit) == 0u) break;
             // first codeword longer than the table window, or the end mark
             acc -= kLutMiss;
-            const u32 next_be = k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : be32(next_unit_word0);
+            const u32 next_be = be32(k + 1 < kUnitWords ? cu.w[(k + 1) % kUnitWords] : next_unit_word0);
             const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutCBits, 1>(hi, lo, next_be, acc));
             if ((sl >> 8) == u32(GH_EOF_SYMBOL)) {
               if (!neof) first_eof = count + (acc >> kCurShift);
@@ -447,12 +447,10 @@ __device__ __forceinline__ bool speculate_subsequence(SmemSpeculate& s, const De
       // two unit buffers that swap roles, so the unit in flight is never copied (a copy would wait for the load)
       Unit8 ua = ldg_unit(g.payload + 32 * u, aligned32), ub;
       while (true) {
-        unit_to_stream_order(ua);
         ub = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
         walk_unit(ua, ub.w[0]);
         if (u == ulast) break;
         ++u;
-        unit_to_stream_order(ub);
         ua = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
         walk_unit(ub, ua.w[0]);
         if (u == ulast) break;

@@ -52,7 +52,9 @@ constexpr int kEncTicketSubTile = GH_ENC_TICKET_SUBTILE;  // sub-tile during whi
 //  * The (codeword, length) table is REPLICATED across the banks so that the per-byte gather is (nearly) free of
 //    bank conflicts: with one copy, 32 lanes looking up 32 random bytes cost ~4 wavefronts per LDS and the L1 data
 //    pipe was as busy as the ALUs (profiles/r2b: 262 M shared-load wavefronts for 67 M lookups).
-//      variant 4: 32-bit entries  code << 16 | len, 16 copies: word (sym * 16 + lane % 16)             -- 16 KiB
+//      variant 4: 64-bit entries  (code << 16 | len, 1 << len), 8 copies: slot (sym * 8 + lane % 8)     -- 16 KiB
+//                 (the power of two lets the packer concatenate with multiply-adds on the FMA pipe instead of
+//                 funnel shifts on the ALU pipe, which is the pipe this kernel saturates)
 //      variant 2: 64-bit entries (len << 32) | code,  4 copies: slot (sym * 4 + lane % 4)              --  8 KiB
 //    Lanes that share a copy are served by one broadcast when their bytes are equal, else serially.
 //  * staging: worst case per sub-tile = 4096 symbols x max code length (+ end mark, + slack for the funnel shift).
@@ -62,8 +64,8 @@ struct EncSmem {
   static constexpr int kMaxLen = kSymsPerChunk == 4 ? 16 : 32;
   static constexpr int kStageWords = (kEncSubTileBytes * kMaxLen + 32 + 31) / 32 + 2;
   static constexpr int kBuffers = kSymsPerChunk == 4 ? 3 : 2;
-  static constexpr int kCopies = kSymsPerChunk == 4 ? 16 : 4;
-  static constexpr int kEntryBytes = kSymsPerChunk == 4 ? 4 : 8;
+  static constexpr int kCopies = kSymsPerChunk == 4 ? 8 : 4;
+  static constexpr int kEntryBytes = 8;
   static constexpr int kSymStride = kCopies * kEntryBytes;  // bytes between consecutive symbols' entries
   static constexpr int kLutWords = 256 * kSymStride / 4;
   u32 lut[kLutWords];
@@ -104,12 +106,14 @@ __device__ __forceinline__ void stage_bits(u32* stage, u32 pos, u64 acc, u32 len
   const u32 lo = u32(acc), hi = u32(acc >> 32);
   atomicOr(stage + w_last, lo << r);
   if (w_last > w_first) atomicOr(stage + w_last - 1, __funnelshift_l(lo, hi, r));
-  if (w_last > w_first + 1) atomicOr(stage + w_last - 2, r ? hi >> (32 - r) : 0u);
+  if (w_last > w_first + 1) atomicOr(stage + w_last - 2, __funnelshift_l(hi, 0u, r));  // hi >> (32 - r), 0 when r == 0
 }
 
+// byte k of a 16-byte vector, zero-extended: one PRMT (the scaling to a table offset is then an IMAD on the FMA pipe;
+// as shift + mask the extraction costs two instructions on the ALU pipe, which is the pipe this kernel saturates)
 __device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
   const u32 w = (k >> 2) == 0 ? v.x : (k >> 2) == 1 ? v.y : (k >> 2) == 2 ? v.z : v.w;
-  return (w >> (8 * (k & 3))) & 0xffu;
+  return __byte_perm(w, 0u, 0x4440u | u32(k & 3));
 }
 
 // gather from this lane's copy of the table (see EncSmem)
@@ -151,7 +155,8 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   for (unsigned i = t; i < 256u * Smem::kCopies; i += kEncThreads) {
     const unsigned sym = i / Smem::kCopies;
     if (kSymsPerChunk == 4) {
-      sm.lut[i] = (table.codeword[sym] << 16) | table.length[sym];
+      sm.lut[2 * i] = (table.codeword[sym] << 16) | table.length[sym];
+      sm.lut[2 * i + 1] = 1u << table.length[sym];
     } else {
       sm.lut[2 * i] = table.codeword[sym];
       sm.lut[2 * i + 1] = table.length[sym];
@@ -280,22 +285,22 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
             u64 acc = 0;
             u32 clen = 0;
             if (kSymsPerChunk == 4) {
-              // entries are code << 16 | len with len <= 16: the funnel shifts take the entry itself as distance
-              // (they use it modulo 32), and the lengths are summed as whole entries and masked once
-              u32 lo = 0, hi = 0, esum = 0;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const u32 e = lut_word<4>(lut_lane, vec_byte(raw[j], c * 4 + q));
-                if (q == 0) {
-                  lo = e >> 16;
-                } else {
-                  hi = __funnelshift_l(lo, hi, e);
-                  lo = __funnelshift_l(0u, lo, e) | (e >> 16);
-                }
-                esum += e;
-              }
-              acc = (u64(hi) << 32) | lo;
-              clen = esum & 0xffffu;
+              // entries are (code << 16 | len, 1 << len) with len <= 16. acc = acc * 2^len + code, all on the FMA
+              // pipe: the code is the high half of the entry (IMAD.HI), the products are IMAD / IMAD.WIDE, and adding
+              // the code cannot carry because the product's low len bits are zero. Lengths are summed as whole
+              // entries (they are the low halves and cannot carry into the codes) and masked once.
+              const uint2 e0 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 0) * u32(Smem::kSymStride));
+              const uint2 e1 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 1) * u32(Smem::kSymStride));
+              const uint2 e2 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 2) * u32(Smem::kSymStride));
+              const uint2 e3 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 3) * u32(Smem::kSymStride));
+              const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
+              const u64 p2 = u64(a01) * e2.y;                                               // <= 48 bits
+              const u32 lo2 = u32(p2) + __umulhi(e2.x, 1u << 16), hi2 = u32(p2 >> 32);
+              const u64 p3 = u64(lo2) * e3.y;
+              const u32 lo3 = u32(p3) + __umulhi(e3.x, 1u << 16);
+              const u32 hi3 = hi2 * e3.y + u32(p3 >> 32);
+              acc = (u64(hi3) << 32) | lo3;
+              clen = (e0.x + e1.x + e2.x + e3.x) & 0xffffu;
             } else {
 #pragma unroll
               for (int q = 0; q < kSymsPerChunk; ++q) {

@@ -87,6 +87,7 @@ struct DecControl {  // device-resident, copied back to the host after each roun
   u32 eof_prefix;     // symbols before the first end mark inside subsequence eof_index
   u32 fine;           // 1: fine-grained pipeline (2 KiB segments, piece states valid)
   u32 work_count;     // entries appended to the next re-walk list in this round
+  u32 phase;          // 1: synchronised by the phase walk (8/9-bit codes)
 };
 
 struct DecWorkspace {
@@ -102,6 +103,14 @@ struct DecWorkspace {
   u64* out_off;    // [n_sub]  output offset of each subsequence's first symbol
   u32* pieces;     // [32 * n_sub] fine pipeline only: state of each 64-byte piece
   u32* work[2];    // [n_sub] each: subsequences to re-walk in this / the next round (near-fixed-length codes)
+  // phase walk (8/9-bit codes), subsequences of >= kPhaseMinSub bytes: per subsequence the transfer function
+  // entry -> exit (9 x 4 bits) and, per entry, codeword count / first end mark / end marks
+  u64* ph_fn;
+  u32* ph_cnt;
+  u32* ph_first;
+  u32* ph_neof;
+  u64* ph_tile_fn;   // composition over kPhaseTile subsequences
+  u32* ph_tile_entry;
   u64* tile_sum;   // [n_tiles]
   u64* tile_base;  // [n_tiles]
 };
@@ -641,6 +650,158 @@ dec_sync_kernel(DecGeometry g, DecWorkspace ws) {
   // coarser subsequences (an exit that depends on the entry means the paths did not meet inside the subsequence)
   const unsigned moved = __ballot_sync(0xffffffffu, exit_moved);
   if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&ws.ctl->exits_changed, u32(__popc(moved)));
+}
+
+// ---- K5c: phase walk for codes of 8 and 9 bits only (uniform-looking bytes) ---------------------------------
+// With lengths {8, 9} and the 9-bit codewords being exactly those whose first 8 bits are zero (first_code_[8] == 1:
+// the reference's canonical convention makes the longest codes the numerically smallest), a path advances 8 bits
+// per codeword and changes phase only where 8 zero bits start ON its phase. Such paths take thousands of symbols to
+// meet (profiles: ~5.7k), so the fixed-point rounds of K5a/K5b degenerate -- ten rounds, each one serial walk of a
+// whole subsequence. Here a thread instead finds the (sparse) positions of 8 zero bits in its subsequence with a
+// few logic ops per 32-bit word, replays ALL nine possible entries 0..8 over those events at once, and stores the
+// subsequence's transfer function entry -> exit (9 x 4 bits) with the per-entry counts. The functions are then
+// composed by a scan (they are associative), which yields every subsequence's true entry with no rounds at all.
+constexpr int kPhasePaths = 9;
+constexpr u32 kPhaseMinSub = 1024;
+constexpr int kPhaseTile = 64;
+constexpr int kPhaseScanThreads = 1024;
+
+__host__ __device__ inline u32 fn_get(u64 f, u32 e) { return u32(f >> (4 * e)) & 15u; }
+__host__ __device__ inline u64 fn_identity() {
+  u64 f = 0;
+  for (u32 e = 0; e < u32(kPhasePaths); ++e) f |= u64(e) << (4 * e);
+  return f;
+}
+__host__ __device__ inline u64 fn_then(u64 f, u64 g) {  // e -> g(f(e))
+  u64 r = 0;
+  for (u32 e = 0; e < u32(kPhasePaths); ++e) r |= u64(fn_get(g, fn_get(f, e))) << (4 * e);
+  return r;
+}
+
+__global__ void __launch_bounds__(kDecThreads)
+dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
+  const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  if (i >= g.n_sub) return;
+  const u64 start = i * u64(g.sub_bytes) * 8;
+  const u32 end = u32(sub_end_bits(g, i));
+  const bool collapsed = i == 0 && g.entry0 > 8u;  // the image's first codeword may sit far into its first sector
+  u32 ready[kPhasePaths], nlong[kPhasePaths], neof[kPhasePaths], first[kPhasePaths];
+#pragma unroll
+  for (int p = 0; p < kPhasePaths; ++p) {
+    ready[p] = collapsed ? g.entry0 : u32(p);
+    nlong[p] = 0, neof[p] = 0, first[p] = kNoEof;
+  }
+  const u64 full_vecs = g.readable >> 4;
+  const u64 v0 = start >> 7;
+  const u32 nwords = (end + 31u) >> 5;
+  auto load_vec = [&](u64 v) -> uint4 {
+    return v < full_vecs ? ldg128(reinterpret_cast<const uint4*>(g.payload) + v) : fetch_tail(g.payload, g.readable, v);
+  };
+  uint4 cur = load_vec(v0), nxt = load_vec(v0 + 1);
+  for (u32 j0 = 0; j0 < nwords; j0 += 4) {
+    const uint4 ahead = load_vec(v0 + (j0 >> 2) + 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const u32 j = j0 + u32(k);
+      if (j < nwords) {
+        const u32 w_hi = be32(k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w);
+        const u32 w_lo = be32(k == 0 ? cur.y : k == 1 ? cur.z : k == 2 ? cur.w : nxt.x);
+        const u64 V = (u64(w_hi) << 32) | w_lo;
+        u64 r = ~V;         // ones where the stream has zeros; stream position b of this word is bit 63 - b
+        r &= r << 1;        // ... and the next position too
+        r &= r << 2;
+        r &= r << 4;        // bit 63 - b set: positions b .. b + 7 are all zero
+        u32 m = u32(r >> 32);
+        const u32 base = j << 5;
+        if (base + 32u > end) m &= ~(0xffffffffu >> (end - base));  // only codewords that start before `end`
+        while (m) {
+          const u32 b = u32(__clz(int(m)));
+          m &= ~(0x80000000u >> b);
+          const u32 x = base + b;
+          const u32 eofbit = u32(V >> (55u - b)) & 1u;  // the ninth bit of the codeword
+#pragma unroll
+          for (int p = 0; p < kPhasePaths; ++p) {
+            if (((ready[p] ^ x) & 7u) == 0u && ready[p] <= x) {  // x is a codeword start of this path
+              if (eofbit == eof_v) {
+                if (!neof[p]) first[p] = (x - (collapsed ? g.entry0 : u32(p)) - nlong[p]) >> 3;
+                ++neof[p];
+              }
+              ++nlong[p];
+              ready[p] = x + 9u;
+            }
+          }
+        }
+      }
+    }
+    cur = nxt;
+    nxt = ahead;
+  }
+  u64 fn = 0;
+#pragma unroll
+  for (int p = 0; p < kPhasePaths; ++p) {
+    u32 q = ready[p];
+    if (q < end) q += ((end - q + 7u) >> 3) << 3;
+    const u32 e_p = collapsed ? g.entry0 : u32(p);
+    fn |= u64(q - end) << (4 * p);
+    ws.ph_cnt[i * kPhasePaths + p] = q > e_p ? (q - e_p - nlong[p]) >> 3 : 0u;
+    ws.ph_first[i * kPhasePaths + p] = first[p];
+    ws.ph_neof[i * kPhasePaths + p] = neof[p];
+  }
+  ws.ph_fn[i] = fn;
+}
+
+__global__ void __launch_bounds__(kDecThreads)
+dec_phase_tiles_kernel(DecGeometry g, DecWorkspace ws) {
+  const u64 t = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  const u64 first = t * kPhaseTile;
+  if (first >= g.n_sub) return;
+  u64 f = fn_identity();
+  for (u64 i = first; i < first + kPhaseTile && i < g.n_sub; ++i) f = fn_then(f, ws.ph_fn[i]);
+  ws.ph_tile_fn[t] = f;
+}
+
+// one block: scan of the tile functions -> entry of every tile
+__global__ void __launch_bounds__(kPhaseScanThreads)
+dec_phase_scan_kernel(DecGeometry g, DecWorkspace ws) {
+  __shared__ u64 s_f[kPhaseScanThreads];
+  const unsigned t = threadIdx.x;
+  const u64 n_tiles = (g.n_sub + kPhaseTile - 1) / kPhaseTile;
+  const u64 per = (n_tiles + kPhaseScanThreads - 1) / kPhaseScanThreads;
+  const u64 lo = u64(t) * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+  u64 f = fn_identity();
+  for (u64 k = lo; k < hi; ++k) f = fn_then(f, ws.ph_tile_fn[k]);
+  s_f[t] = f;
+  __syncthreads();
+  for (unsigned d = 1; d < unsigned(kPhaseScanThreads); d <<= 1) {  // inclusive scan, earlier functions first
+    const u64 left = t >= d ? s_f[t - d] : fn_identity();
+    __syncthreads();
+    if (t >= d) s_f[t] = fn_then(left, s_f[t]);
+    __syncthreads();
+  }
+  const u64 before = t ? s_f[t - 1] : fn_identity();
+  u32 e = fn_get(before, g.entry0 > 8u ? 0u : g.entry0);
+  for (u64 k = lo; k < hi; ++k) {
+    ws.ph_tile_entry[k] = e;
+    e = fn_get(ws.ph_tile_fn[k], e);
+  }
+}
+
+// the chosen entry's results become the subsequence states that K6/K7 work from
+__global__ void __launch_bounds__(kDecThreads)
+dec_phase_finish_kernel(DecGeometry g, DecWorkspace ws) {
+  const u64 t = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  const u64 first = t * kPhaseTile;
+  if (first >= g.n_sub) return;
+  u32 e = ws.ph_tile_entry[t];
+  for (u64 i = first; i < first + kPhaseTile && i < g.n_sub; ++i) {
+    const u32 exit = fn_get(ws.ph_fn[i], e);
+    const u64 k = i * kPhasePaths + e;
+    const u32 neof = ws.ph_neof[k];
+    ws.neof[i] = neof;
+    ws.eofpos[i] = ws.ph_first[k];
+    ws.sub[i] = pack_state(ws.ph_cnt[k], i == 0 ? g.entry0 : e, exit, neof != 0);
+    e = exit;
+  }
 }
 
 // ---- K6: truncate at the first end mark, turn counts into output offsets -----------------------------------
@@ -1260,7 +1421,7 @@ static int set_fine_attrs() {  // opt-in to > 48 KB of dynamic shared memory for
 }
 
 struct DecLayout {
-  size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_pieces, off_work0, off_work1, off_tile_sum, off_tile_base, total;
+  size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_pieces, off_work0, off_work1, off_ph_fn, off_ph_cnt, off_ph_first, off_ph_neof, off_ph_tile_fn, off_ph_tile_entry, off_tile_sum, off_tile_base, total;
 };
 
 static DecLayout dec_layout(u64 slice_bytes) {
@@ -1281,7 +1442,14 @@ static DecLayout dec_layout(u64 slice_bytes) {
   L.off_pieces = L.off_out_off + up(size_t(max_sub) * 8);
   L.off_work0 = L.off_pieces + up((size_t(slice_bytes) / kFineSubBytes + 2) * 32 * 4);
   L.off_work1 = L.off_work0 + up(size_t(max_sub) * 4);
-  L.off_tile_sum = L.off_work1 + up(size_t(max_sub) * 4);
+  const u64 ph_sub = slice_bytes / kPhaseMinSub + 2, ph_tiles = ph_sub / kPhaseTile + 2;
+  L.off_ph_fn = L.off_work1 + up(size_t(max_sub) * 4);
+  L.off_ph_cnt = L.off_ph_fn + up(size_t(ph_sub) * 8);
+  L.off_ph_first = L.off_ph_cnt + up(size_t(ph_sub) * kPhasePaths * 4);
+  L.off_ph_neof = L.off_ph_first + up(size_t(ph_sub) * kPhasePaths * 4);
+  L.off_ph_tile_fn = L.off_ph_neof + up(size_t(ph_sub) * kPhasePaths * 4);
+  L.off_ph_tile_entry = L.off_ph_tile_fn + up(size_t(ph_tiles) * 8);
+  L.off_tile_sum = L.off_ph_tile_entry + up(size_t(ph_tiles) * 4);
   L.off_tile_base = L.off_tile_sum + up(size_t(max_tiles) * 8);
   L.total = L.off_tile_base + up(size_t(max_tiles) * 8);
   return L;
@@ -1303,6 +1471,12 @@ static DecWorkspace dec_bind(void* d_ws, const DecLayout& L) {
   w.pieces = reinterpret_cast<u32*>(p + L.off_pieces);
   w.work[0] = reinterpret_cast<u32*>(p + L.off_work0);
   w.work[1] = reinterpret_cast<u32*>(p + L.off_work1);
+  w.ph_fn = reinterpret_cast<u64*>(p + L.off_ph_fn);
+  w.ph_cnt = reinterpret_cast<u32*>(p + L.off_ph_cnt);
+  w.ph_first = reinterpret_cast<u32*>(p + L.off_ph_first);
+  w.ph_neof = reinterpret_cast<u32*>(p + L.off_ph_neof);
+  w.ph_tile_fn = reinterpret_cast<u64*>(p + L.off_ph_tile_fn);
+  w.ph_tile_entry = reinterpret_cast<u32*>(p + L.off_ph_tile_entry);
   w.tile_sum = reinterpret_cast<u64*>(p + L.off_tile_sum);
   w.tile_base = reinterpret_cast<u64*>(p + L.off_tile_base);
   return w;
@@ -1370,6 +1544,52 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     g.sub_bytes = h_ctl.sub_bytes;
     fine = h_ctl.fine != 0;
     if (g.sub_bytes < kMinSubBytes || (g.sub_bytes % kMinSubBytes)) return GH_ERR_ARG;
+  }
+  // Codes of 8 and 9 bits only whose 9-bit codewords are those with eight leading zeros: phase walk (K5c), no rounds.
+  bool phase = false;
+  u32 eof_v = 2;  // value of the end mark's ninth bit (2: the end mark is not a 9-bit codeword)
+  if (code->min_len == 8 && code->max_len == 9 && code->first_code[8] == 1 && code->first_code[9] == 0 &&
+      slice_bytes >= 4 * kPhaseMinSub && pipeline_choice() != 2 && !getenv("GH_NO_PHASE_WALK")) {
+    phase = first_call ? true : h_ctl.phase != 0;
+    for (u32 v = 0; v < 2; ++v) {
+      const u32 idx = code->start_pos[9] + v;
+      if (idx < u32(GH_NSYM) && code->symbol[idx] == u32(GH_EOF_SYMBOL)) eof_v = v;
+    }
+  }
+  if (phase) {
+    if (first_call) {  // no reason for coarse subsequences here: the phase walk needs no path to meet another
+      g.sub_bytes = choose_sub_bytes(slice_bytes);
+      if (g.sub_bytes < kPhaseMinSub) g.sub_bytes = kPhaseMinSub;
+      fine = false;
+    }
+    g.n_sub = (slice_bytes + g.sub_bytes - 1) / g.sub_bytes;
+    const unsigned blocks = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
+    const u64 n_tiles = (g.n_sub + kPhaseTile - 1) / kPhaseTile;
+    const unsigned tile_blocks = unsigned((n_tiles + kDecThreads - 1) / kDecThreads);
+    h_ctl = DecControl();
+    h_ctl.eof_index = kNoEof;
+    h_ctl.sub_bytes = g.sub_bytes;
+    h_ctl.n_sub = g.n_sub;
+    h_ctl.phase = 1u;
+    GH_CUDA_TRY(cudaMemcpyAsync(ws.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, stream));
+    GH_LAUNCH(dec_phase_walk_kernel, blocks, kDecThreads, 0, stream, g, ws, eof_v);
+    GH_LAUNCH(dec_phase_tiles_kernel, tile_blocks, kDecThreads, 0, stream, g, ws);
+    GH_LAUNCH(dec_phase_scan_kernel, 1, kPhaseScanThreads, 0, stream, g, ws);
+    GH_LAUNCH(dec_phase_finish_kernel, tile_blocks, kDecThreads, 0, stream, g, ws);
+    int rc = check_launch();
+    if (rc != GH_OK) return rc;
+    rc = dec_finish(g, ws, &h_ctl, stream);
+    if (rc != GH_OK) return rc;
+    if (result) {
+      result->n_symbols = h_ctl.total;
+      result->exit_bit = h_ctl.exit_bit;
+      result->eof_found = h_ctl.eof_found;
+      result->rounds = 1;
+      result->sub_bytes = g.sub_bytes;
+    }
+    if (geom_out) *geom_out = g;
+    if (fine_out) *fine_out = false;
+    return GH_OK;
   }
   // Synchronisation rounds until a clean one. Round k makes subsequences 0..k exact whatever the data, so this
   // terminates after at most n_sub rounds; with codes that self-synchronise it takes two or three.

@@ -43,8 +43,12 @@ constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
 #define GH_ENC_LOOK_DEPTH 1
 #endif
 #ifndef GH_ENC_TICKET_SUBTILE
-#define GH_ENC_TICKET_SUBTILE 2
+#define GH_ENC_TICKET_SUBTILE 3
 #endif
+#ifndef GH_ENC_POLL_SLEEP_NS
+#define GH_ENC_POLL_SLEEP_NS 0
+#endif
+constexpr unsigned kEncPollSleepNs = GH_ENC_POLL_SLEEP_NS;  // pause between two polls of an unpublished tile state
 constexpr int kEncLookDepth = GH_ENC_LOOK_DEPTH;        // look-back rounds whose loads are in flight together
 constexpr int kEncTicketSubTile = GH_ENC_TICKET_SUBTILE;  // sub-tile during which the block draws its next tile
 
@@ -246,25 +250,36 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
         long long look = (long long)tile - 1;
         bool done = false;
         while (!done) {
-          // kEncLookDepth x 32 predecessors per L2 round trip: all loads are issued before the first is examined
+          // One round trip covers 32 x kEncLookDepth predecessors: lane l owns the kEncLookDepth consecutive tiles
+          // look - l * kEncLookDepth - r (r = 0 nearest), loads all of them at once, folds them locally (sum of
+          // aggregates up to and including its nearest PREFIX) and the warp then needs ONE ballot + ONE sum.
+          // The kernel's throughput is capped at (tiles covered per round) / (round time): tiles that cannot find
+          // a prefix in a round queue up behind those that can, so the window per round is what has to be wide.
+          const long long first_idx = look - (long long)lane * kEncLookDepth;
           u64 st[kEncLookDepth];
 #pragma unroll
           for (int r = 0; r < kEncLookDepth; ++r) {
-            const long long idx = look - (long long)lane - 32 * r;
+            const long long idx = first_idx - r;
             st[r] = idx >= 0 ? ld_volatile_u64(ws.tile_state + idx) : kFlagPrefix;  // virtual tiles before tile 0 add nothing
           }
+          u64 local = 0;
+          bool local_prefix = false;
 #pragma unroll
           for (int r = 0; r < kEncLookDepth; ++r) {
-            if (done) break;
-            const long long idx = look - (long long)lane - 32 * r;
-            while ((st[r] & kFlagMask) == 0) st[r] = ld_volatile_u64(ws.tile_state + idx);  // not published yet
-            const unsigned has_prefix = __ballot_sync(0xffffffffu, (st[r] & kFlagMask) == kFlagPrefix);
-            // lanes up to and including the nearest tile that already knows its prefix contribute
-            const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
-            const u64 contrib = (has_prefix == 0 || lane <= first) ? (st[r] & ~kFlagMask) : 0ull;
-            exclusive += warp_sum64(contrib);
-            done = has_prefix != 0;
+            const long long idx = first_idx - r;
+            while ((st[r] & kFlagMask) == 0) {  // not published yet
+              if (kEncPollSleepNs) __nanosleep(kEncPollSleepNs);
+              st[r] = ld_volatile_u64(ws.tile_state + idx);
+            }
+            if (!local_prefix) local += st[r] & ~kFlagMask;
+            local_prefix = local_prefix || (st[r] & kFlagMask) == kFlagPrefix;
           }
+          const unsigned has_prefix = __ballot_sync(0xffffffffu, local_prefix);
+          // lanes up to and including the nearest one that found a prefix contribute
+          const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
+          const u64 contrib = (has_prefix == 0 || lane <= first) ? local : 0ull;
+          exclusive += warp_sum64(contrib);
+          done = has_prefix != 0;
           look -= 32 * kEncLookDepth;
         }
         if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
@@ -363,6 +378,9 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       }
       before += nbits;
     }
+    // the next tile's number was written after barrier (c_3) when it is drawn during the last sub-tile: one more
+    // barrier before it is read (the two-buffer variant has (d_3) for that)
+    if (Smem::kBuffers == 3 && kEncTicketSubTile == kEncSubTiles - 1) __syncthreads();
   }
 }
 

@@ -678,10 +678,17 @@ __host__ __device__ inline u64 fn_then(u64 f, u64 g) {  // e -> g(f(e))
   return r;
 }
 
+// Events (positions where eight zero bits start, with the ninth bit) are first collected in a per-thread list in
+// shared memory and replayed over the nine paths in batches: found one at a time, an event costs the whole warp the
+// nine-path update whenever ANY lane has one in its current word (almost always), which made this kernel 5x slower.
+constexpr int kPhaseListLen = 15;  // replay threshold; a word adds at most 32 events: 47 rows x 256 threads x 4 B = 47 KiB
+
 __global__ void __launch_bounds__(kDecThreads)
 dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
+  __shared__ u32 s_list[kPhaseListLen + 32][kDecThreads];  // [k][thread]: bank = thread % 32, conflict-free
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
   if (i >= g.n_sub) return;
+  const unsigned t = threadIdx.x;
   const u64 start = i * u64(g.sub_bytes) * 8;
   const u32 end = u32(sub_end_bits(g, i));
   const bool collapsed = i == 0 && g.entry0 > 8u;  // the image's first codeword may sit far into its first sector
@@ -691,6 +698,25 @@ dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
     ready[p] = collapsed ? g.entry0 : u32(p);
     nlong[p] = 0, neof[p] = 0, first[p] = kNoEof;
   }
+  u32 n_ev = 0;
+  auto replay = [&]() {
+    for (u32 k = 0; k < n_ev; ++k) {
+      const u32 ev = s_list[k][t];
+      const u32 x = ev & 0x7fffffffu, eofbit = ev >> 31;
+#pragma unroll
+      for (int p = 0; p < kPhasePaths; ++p) {
+        if (((ready[p] ^ x) & 7u) == 0u && ready[p] <= x) {  // x is a codeword start of this path
+          if (eofbit == eof_v) {
+            if (!neof[p]) first[p] = (x - (collapsed ? g.entry0 : u32(p)) - nlong[p]) >> 3;
+            ++neof[p];
+          }
+          ++nlong[p];
+          ready[p] = x + 9u;
+        }
+      }
+    }
+    n_ev = 0;
+  };
   const u64 full_vecs = g.readable >> 4;
   const u64 v0 = start >> 7;
   const u32 nwords = (end + 31u) >> 5;
@@ -714,28 +740,18 @@ dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
         u32 m = u32(r >> 32);
         const u32 base = j << 5;
         if (base + 32u > end) m &= ~(0xffffffffu >> (end - base));  // only codewords that start before `end`
-        while (m) {
+        while (m) {  // at most 32 per word: the list has 32 spare entries above the replay threshold
           const u32 b = u32(__clz(int(m)));
           m &= ~(0x80000000u >> b);
-          const u32 x = base + b;
-          const u32 eofbit = u32(V >> (55u - b)) & 1u;  // the ninth bit of the codeword
-#pragma unroll
-          for (int p = 0; p < kPhasePaths; ++p) {
-            if (((ready[p] ^ x) & 7u) == 0u && ready[p] <= x) {  // x is a codeword start of this path
-              if (eofbit == eof_v) {
-                if (!neof[p]) first[p] = (x - (collapsed ? g.entry0 : u32(p)) - nlong[p]) >> 3;
-                ++neof[p];
-              }
-              ++nlong[p];
-              ready[p] = x + 9u;
-            }
-          }
+          s_list[n_ev++][t] = (base + b) | ((u32(V >> (55u - b)) & 1u) << 31);  // position | ninth bit of the codeword
         }
+        if (n_ev >= u32(kPhaseListLen)) replay();
       }
     }
     cur = nxt;
     nxt = ahead;
   }
+  replay();
   u64 fn = 0;
 #pragma unroll
   for (int p = 0; p < kPhasePaths; ++p) {
@@ -786,22 +802,36 @@ dec_phase_scan_kernel(DecGeometry g, DecWorkspace ws) {
   }
 }
 
-// the chosen entry's results become the subsequence states that K6/K7 work from
+// every subsequence's entry: thread = tile, a serial walk over its (independent, batched) function loads
 __global__ void __launch_bounds__(kDecThreads)
-dec_phase_finish_kernel(DecGeometry g, DecWorkspace ws) {
+dec_phase_entries_kernel(DecGeometry g, DecWorkspace ws, u32* __restrict__ entry_out) {
   const u64 t = u64(blockIdx.x) * kDecThreads + threadIdx.x;
   const u64 first = t * kPhaseTile;
   if (first >= g.n_sub) return;
   u32 e = ws.ph_tile_entry[t];
-  for (u64 i = first; i < first + kPhaseTile && i < g.n_sub; ++i) {
-    const u32 exit = fn_get(ws.ph_fn[i], e);
-    const u64 k = i * kPhasePaths + e;
-    const u32 neof = ws.ph_neof[k];
-    ws.neof[i] = neof;
-    ws.eofpos[i] = ws.ph_first[k];
-    ws.sub[i] = pack_state(ws.ph_cnt[k], i == 0 ? g.entry0 : e, exit, neof != 0);
-    e = exit;
+  for (u64 i0 = first; i0 < first + kPhaseTile && i0 < g.n_sub; i0 += 8) {
+    u64 f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = i0 + k < g.n_sub ? ws.ph_fn[i0 + k] : fn_identity();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (i0 + k < g.n_sub) entry_out[i0 + k] = e;
+      e = fn_get(f[k], e);
+    }
   }
+}
+
+// the chosen entry's results become the subsequence states that K6/K7 work from
+__global__ void __launch_bounds__(kDecThreads)
+dec_phase_finish_kernel(DecGeometry g, DecWorkspace ws, const u32* __restrict__ entry_in) {
+  const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
+  if (i >= g.n_sub) return;
+  const u32 e = entry_in[i];
+  const u64 k = i * kPhasePaths + e;
+  const u32 neof = ws.ph_neof[k];
+  ws.neof[i] = neof;
+  ws.eofpos[i] = ws.ph_first[k];
+  ws.sub[i] = pack_state(ws.ph_cnt[k], i == 0 ? g.entry0 : e, fn_get(ws.ph_fn[i], e), neof != 0);
 }
 
 // ---- K6: truncate at the first end mark, turn counts into output offsets -----------------------------------
@@ -1575,7 +1605,8 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     GH_LAUNCH(dec_phase_walk_kernel, blocks, kDecThreads, 0, stream, g, ws, eof_v);
     GH_LAUNCH(dec_phase_tiles_kernel, tile_blocks, kDecThreads, 0, stream, g, ws);
     GH_LAUNCH(dec_phase_scan_kernel, 1, kPhaseScanThreads, 0, stream, g, ws);
-    GH_LAUNCH(dec_phase_finish_kernel, tile_blocks, kDecThreads, 0, stream, g, ws);
+    GH_LAUNCH(dec_phase_entries_kernel, tile_blocks, kDecThreads, 0, stream, g, ws, ws.work[0]);
+    GH_LAUNCH(dec_phase_finish_kernel, blocks, kDecThreads, 0, stream, g, ws, (const u32*)ws.work[0]);
     int rc = check_launch();
     if (rc != GH_OK) return rc;
     rc = dec_finish(g, ws, &h_ctl, stream);

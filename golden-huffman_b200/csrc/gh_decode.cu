@@ -687,10 +687,10 @@ __global__ void __launch_bounds__(kDecThreads)
 dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
   __shared__ u32 s_list[kPhaseListLen + 32][kDecThreads];  // [k][thread]: bank = thread % 32, conflict-free
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
-  if (i >= g.n_sub) return;
+  const bool live = i < g.n_sub;  // every lane stays for the warp-wide votes below
   const unsigned t = threadIdx.x;
   const u64 start = i * u64(g.sub_bytes) * 8;
-  const u32 end = u32(sub_end_bits(g, i));
+  const u32 end = live ? u32(sub_end_bits(g, i)) : 0u;
   const bool collapsed = i == 0 && g.entry0 > 8u;  // the image's first codeword may sit far into its first sector
   u32 ready[kPhasePaths], nlong[kPhasePaths], neof[kPhasePaths], first[kPhasePaths];
 #pragma unroll
@@ -720,11 +720,17 @@ dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
   const u64 full_vecs = g.readable >> 4;
   const u64 v0 = start >> 7;
   const u32 nwords = (end + 31u) >> 5;
+  u32 nwords_warp = nwords;  // warp-uniform loop bound: the replay below is entered by all lanes together
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const u32 other = __shfl_xor_sync(0xffffffffu, nwords_warp, d);
+    nwords_warp = other > nwords_warp ? other : nwords_warp;
+  }
   auto load_vec = [&](u64 v) -> uint4 {
     return v < full_vecs ? ldg128(reinterpret_cast<const uint4*>(g.payload) + v) : fetch_tail(g.payload, g.readable, v);
   };
   uint4 cur = load_vec(v0), nxt = load_vec(v0 + 1);
-  for (u32 j0 = 0; j0 < nwords; j0 += 4) {
+  for (u32 j0 = 0; j0 < nwords_warp; j0 += 4) {
     const uint4 ahead = load_vec(v0 + (j0 >> 2) + 2);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -745,13 +751,16 @@ dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
           m &= ~(0x80000000u >> b);
           s_list[n_ev++][t] = (base + b) | ((u32(V >> (55u - b)) & 1u) << 31);  // position | ninth bit of the codeword
         }
-        if (n_ev >= u32(kPhaseListLen)) replay();
       }
+      // replay when ANY lane's list is getting full, all lanes together: entered lane by lane, the replay loop
+      // would run once per lane instead of once per warp
+      if (__any_sync(0xffffffffu, n_ev >= u32(kPhaseListLen))) replay();
     }
     cur = nxt;
     nxt = ahead;
   }
   replay();
+  if (!live) return;
   u64 fn = 0;
 #pragma unroll
   for (int p = 0; p < kPhasePaths; ++p) {

@@ -678,14 +678,15 @@ __host__ __device__ inline u64 fn_then(u64 f, u64 g) {  // e -> g(f(e))
   return r;
 }
 
-// Events (positions where eight zero bits start, with the ninth bit) are first collected in a per-thread list in
-// shared memory and replayed over the nine paths in batches: found one at a time, an event costs the whole warp the
-// nine-path update whenever ANY lane has one in its current word (almost always), which made this kernel 5x slower.
-constexpr int kPhaseListLen = 15;  // replay threshold; a word adds at most 32 events: 47 rows x 256 threads x 4 B = 47 KiB
+// Words that contain events (positions where eight zero bits start) are first collected as records in a per-thread
+// list in shared memory and replayed over the nine paths in batches, all lanes together: handled where they are
+// found, the events cost the whole warp the nine-path update -- or even just a find-first-set loop -- whenever ANY
+// lane has one in its current word (almost always), lane after lane (measured: 1 of 32 lanes active there).
+constexpr int kPhaseListLen = 12;  // records buffered per thread: 12 x 3 words x 256 threads x 4 B = 36 KiB per block
 
 __global__ void __launch_bounds__(kDecThreads)
 dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
-  __shared__ u32 s_list[kPhaseListLen + 32][kDecThreads];  // [k][thread]: bank = thread % 32, conflict-free
+  __shared__ u32 s_list[kPhaseListLen][3][kDecThreads];  // [record][field][thread]: bank = thread % 32
   const u64 i = u64(blockIdx.x) * kDecThreads + threadIdx.x;
   const bool live = i < g.n_sub;  // every lane stays for the warp-wide votes below
   const unsigned t = threadIdx.x;
@@ -698,24 +699,31 @@ dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
     ready[p] = collapsed ? g.entry0 : u32(p);
     nlong[p] = 0, neof[p] = 0, first[p] = kNoEof;
   }
-  u32 n_ev = 0;
+  u32 n_rec = 0;
   auto replay = [&]() {
-    for (u32 k = 0; k < n_ev; ++k) {
-      const u32 ev = s_list[k][t];
-      const u32 x = ev & 0x7fffffffu, eofbit = ev >> 31;
+    for (u32 k = 0; k < n_rec; ++k) {
+      u32 m = s_list[k][0][t];               // event positions of the word, stream position b = bit 31 - b
+      const u32 ninth = s_list[k][1][t];     // stream positions 8 .. 39 of the word's window, same numbering
+      const u32 base = s_list[k][2][t];
+      while (m) {
+        const u32 b = u32(__clz(int(m)));
+        m &= ~(0x80000000u >> b);
+        const u32 x = base + b;
+        const u32 eofbit = (ninth >> (31u - b)) & 1u;  // the ninth bit of the codeword
 #pragma unroll
-      for (int p = 0; p < kPhasePaths; ++p) {
-        if (((ready[p] ^ x) & 7u) == 0u && ready[p] <= x) {  // x is a codeword start of this path
-          if (eofbit == eof_v) {
-            if (!neof[p]) first[p] = (x - (collapsed ? g.entry0 : u32(p)) - nlong[p]) >> 3;
-            ++neof[p];
+        for (int p = 0; p < kPhasePaths; ++p) {
+          if (((ready[p] ^ x) & 7u) == 0u && ready[p] <= x) {  // x is a codeword start of this path
+            if (eofbit == eof_v) {
+              if (!neof[p]) first[p] = (x - (collapsed ? g.entry0 : u32(p)) - nlong[p]) >> 3;
+              ++neof[p];
+            }
+            ++nlong[p];
+            ready[p] = x + 9u;
           }
-          ++nlong[p];
-          ready[p] = x + 9u;
         }
       }
     }
-    n_ev = 0;
+    n_rec = 0;
   };
   const u64 full_vecs = g.readable >> 4;
   const u64 v0 = start >> 7;
@@ -746,15 +754,16 @@ dec_phase_walk_kernel(DecGeometry g, DecWorkspace ws, u32 eof_v) {
         u32 m = u32(r >> 32);
         const u32 base = j << 5;
         if (base + 32u > end) m &= ~(0xffffffffu >> (end - base));  // only codewords that start before `end`
-        while (m) {  // at most 32 per word: the list has 32 spare entries above the replay threshold
-          const u32 b = u32(__clz(int(m)));
-          m &= ~(0x80000000u >> b);
-          s_list[n_ev++][t] = (base + b) | ((u32(V >> (55u - b)) & 1u) << 31);  // position | ninth bit of the codeword
+        if (m) {
+          s_list[n_rec][0][t] = m;
+          s_list[n_rec][1][t] = u32(V >> 24);
+          s_list[n_rec][2][t] = base;
+          ++n_rec;
         }
       }
-      // replay when ANY lane's list is getting full, all lanes together: entered lane by lane, the replay loop
-      // would run once per lane instead of once per warp
-      if (__any_sync(0xffffffffu, n_ev >= u32(kPhaseListLen))) replay();
+      // replay when ANY lane's list is full, all lanes together: entered lane by lane, the replay loop would run
+      // once per lane instead of once per warp
+      if (__any_sync(0xffffffffu, n_rec >= u32(kPhaseListLen))) replay();
     }
     cur = nxt;
     nxt = ahead;

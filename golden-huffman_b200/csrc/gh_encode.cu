@@ -103,6 +103,10 @@ __device__ __noinline__ uint4 load_ragged(const uint8_t* p, int cnt) {
 // position `pos`. Worked from the value's last bit: it is shifted left by the free bits r that remain after it in
 // its last word, which gives the (up to) three words directly -- three shifts, no 64-bit left-justification.
 __device__ __forceinline__ void stage_bits(u32* stage, u32 pos, u64 acc, u32 len) {
+#ifdef GH_PROBE_NO_STAGE  // tuning probe (wrong output): one plain store instead of up to three atomics
+  stage[pos >> 5] = u32(acc) + len;
+  return;
+#endif
   const u32 end = pos + len;           // one past the last bit
   const u32 w_first = pos >> 5;
   const u32 w_last = (end - 1) >> 5;
@@ -199,6 +203,10 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
 #pragma unroll
     for (int j = 0; j < kEncSubTiles; ++j) {
       u32 b = 0;
+#ifdef GH_PROBE_NO_COUNT  // tuning probe (wrong output): no length gather
+      b = 6u * u32(cnt[j]) + (raw[j].x & 1u);
+      if (false)
+#endif
       // variant 4 sums whole entries: the lengths (<= 16 x 16) add up in the low half, the codes above them
       if (cnt[j] == kEncBytesPerThread) {
 #pragma unroll
@@ -249,6 +257,10 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
         exclusive = 0;
         long long look = (long long)tile - 1;
         bool done = false;
+#ifdef GH_PROBE_NO_LOOKBACK  // tuning probe (wrong output): pretend every tile is 6 bits per byte
+        exclusive = start_bit + tile * u64(kEncTileBytes) * 6;
+        done = true;
+#endif
         while (!done) {
           // One round trip covers 32 x kEncLookDepth predecessors: lane l owns the kEncLookDepth consecutive tiles
           // look - l * kEncLookDepth - r (r = 0 nearest), loads all of them at once, folds them locally (sum of
@@ -294,6 +306,9 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       u32* stage = s_stage[buf];
       {
         u32 pos = pos0[j];
+#ifdef GH_PROBE_NO_PACK  // tuning probe (wrong output): no code gather, no concatenation, no staging
+        if (false)
+#endif
         if (cnt[j] == kEncBytesPerThread) {
 #pragma unroll
           for (int c = 0; c < kChunks; ++c) {
@@ -354,14 +369,33 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       const u32 nwords = nbits ? u32((u64(phase) + nbits + pad + 31) >> 5) : 0u;
       const bool partial_end = ((phase + nbits + pad) & 31) != 0;
       const bool shared_head = (j == 0) && (tile > 0) && (phase != 0);
-      for (u32 i = t; i < nwords; i += kEncThreads) {
-        u32 v = __funnelshift_r(stage[i], i ? stage[i - 1] : 0u, phase);
-        const u64 gw = word0 + i;
-        if (pad && gw == (end_bit >> 5)) v |= ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad));
-        if (i == 0 && j > 0 && phase != 0) v |= s_carry[(j - 1) & 1];  // tail of the previous sub-tile
-        if (i == nwords - 1 && partial_end && more_in_tile) s_carry[j & 1] = v;  // continued by the next sub-tile
-        else if (i == 0 && shared_head) ws.head[tile] = v;
-        else if (gw < out_word_cap) out_words[gw] = be32(v);
+#ifdef GH_PROBE_NO_COPYLOOP  // tuning probe (wrong output): no copy-out at all
+      if (false)
+#endif
+      {
+        // interior words (neither the first nor the last of the sub-tile) need none of the special cases: a lean
+        // loop (two LDS, one funnel shift, one byte swap, one store). Measured with the probe builds: the copy-out
+        // loop with all its cases inline cost 0.30 ms of the kernel's 1.73, its global stores almost nothing.
+        const bool fits = word0 + nwords <= out_word_cap;
+        if (fits && nwords > 2u) {
+          u32* const dst = out_words + word0;
+          for (u32 i = t + 1u; i < nwords - 1u; i += kEncThreads) dst[i] = be32(__funnelshift_r(stage[i], stage[i - 1], phase));
+        }
+        // first and last word, and everything when the output might not fit
+        for (u32 i = t; i < nwords; i += kEncThreads) {
+          if (fits && i != 0u && i != nwords - 1u) continue;
+          u32 v = __funnelshift_r(stage[i], i ? stage[i - 1] : 0u, phase);
+          const u64 gw = word0 + i;
+          if (pad && gw == (end_bit >> 5)) v |= ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad));
+          if (i == 0 && j > 0 && phase != 0) v |= s_carry[(j - 1) & 1];  // tail of the previous sub-tile
+          if (i == nwords - 1 && partial_end && more_in_tile) s_carry[j & 1] = v;  // continued by the next sub-tile
+          else if (i == 0 && shared_head) ws.head[tile] = v;
+#ifdef GH_PROBE_NO_COPYOUT  // tuning probe (wrong output): only one word in 64 is stored
+          else if (gw < out_word_cap && (i & 63u) == 0u) out_words[gw] = be32(v);
+#else
+          else if (gw < out_word_cap) out_words[gw] = be32(v);
+#endif
+        }
       }
       if (Smem::kBuffers == 3) {
         // One barrier per sub-tile: the buffer of the PREVIOUS sub-tile is cleared now -- a thread passes barrier

@@ -125,7 +125,8 @@ int gh_encode(const uint8_t* d_in, uint64_t n, const gh_code* code, uint64_t sta
  * decoding and stops at the first end-of-encoding mark on the true decode path.
  * Synchronous with respect to `stream` (the symbol count is returned to the host in *n_out).
  * GH_ERR_SPACE if more than out_cap symbols precede the end mark (*n_out is still set).
- * d_payload must be 16-byte aligned.                                                                */
+ * d_payload must be 16-byte aligned; 32-byte alignment lets the kernels read one whole sector per lane
+ * and request (256-bit loads) instead of two 128-bit loads.                                          */
 size_t gh_decode_workspace_bytes(uint64_t payload_bytes);
 int gh_decode(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code* code, uint8_t* d_out,
               uint64_t out_cap, uint64_t* n_out, void* d_workspace, size_t workspace_bytes, void* stream);

@@ -1016,7 +1016,9 @@ __device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32&
       " @pw mad.lo.u32 %3, %4, %10, 0;\n"
       " @pw mov.u32 %4, %7;\n"
       " mov.b64 a, {%5, %6};\n"
+#ifndef GH_PROBE_W_NOSTORE  // tuning probe (wrong output): everything but the 128-bit store
       " @pg st.global.v4.u32 [a], {%0, %1, %2, %3};\n"
+#endif
       " @pg add.cc.u32 %5, %5, 16;\n"
       " @pg addc.u32 %6, %6, 0;\n"
       "}\n"

@@ -39,6 +39,10 @@ constexpr int kEncSubTileBytes = kEncThreads * kEncBytesPerThread;  // 4 KiB
 constexpr int kEncSubTiles = GH_ENC_SUBTILES;
 constexpr int kEncTileBytes = kEncSubTileBytes * kEncSubTiles;      // 16 KiB per look-back
 constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
+// lean interior copy-out loop: for which variants (measured r3b: helps the short-code variant, not the long-code one)
+#ifndef GH_ENC_LEAN_COPY
+#define GH_ENC_LEAN_COPY(syms_per_chunk) ((syms_per_chunk) == 4)
+#endif
 #ifndef GH_ENC_LOOK_DEPTH
 #define GH_ENC_LOOK_DEPTH 1
 #endif
@@ -376,7 +380,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
         // interior words (neither the first nor the last of the sub-tile) need none of the special cases: a lean
         // loop (two LDS, one funnel shift, one byte swap, one store). Measured with the probe builds: the copy-out
         // loop with all its cases inline cost 0.30 ms of the kernel's 1.73, its global stores almost nothing.
-        const bool fits = word0 + nwords <= out_word_cap;
+        const bool fits = GH_ENC_LEAN_COPY(kSymsPerChunk) && word0 + nwords <= out_word_cap;
         if (fits && nwords > 2u) {
           u32* const dst = out_words + word0;
           for (u32 i = t + 1u; i < nwords - 1u; i += kEncThreads) dst[i] = be32(__funnelshift_r(stage[i], stage[i - 1], phase));

@@ -321,3 +321,31 @@ def test_forced_decode_pipelines(codec, oracle, pipeline):
         assert rc == 0 and nd == len(data) and _bytes(out) == data
     finally:
         codec.lib.lib.gh_debug_select_writer(0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shift", [0, 16])
+@pytest.mark.parametrize("name", ["text", "uniform", "kat3"])
+def test_decode_payload_alignment(codec, oracle, name, shift):
+    """gh_decode takes a payload that is only 16-byte aligned (two 128-bit loads per unit) as well as a 32-byte
+    aligned one (one 256-bit load); `uniform` / `kat3` go through the phase walk of the 8/9-bit code, `text`
+    through speculation + synchronisation rounds. Output identical to the input either way."""
+    import torch
+    import golden_huffman_b200.workloads as w
+    if name == "kat3":
+        data = make_input("kat3_allbytes512")
+        x = _cuda(np.frombuffer(data, dtype=np.uint8))
+    else:
+        x = w.WORKLOADS_TORCH[name]((1 << 22) + 1234, "cuda", seed=5)
+        data = _bytes(x)
+    code = codec.build_code(codec.histogram(x))
+    payload, end_bit = codec.encode(x, code)
+    torch.cuda.synchronize()
+    nbytes = (int(end_bit.item()) + 7) // 8
+    rc, opayload = oracle.encode_payload(data, oracle.build_code(oracle.histogram(data))[1])
+    assert _bytes(payload[:nbytes]) == opayload
+    buf = torch.empty(nbytes + 64 + 256, dtype=torch.uint8, device="cuda")
+    off = (-buf.data_ptr()) % 32 + shift  # 32-byte aligned, or exactly 16 past such a boundary
+    buf[off:off + nbytes].copy_(payload[:nbytes])
+    out, n, rc = codec.decode(buf[off:off + nbytes], nbytes, code, len(data))
+    assert rc == 0 and n == len(data) and _bytes(out[:n]) == data

@@ -43,6 +43,11 @@ constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
 #ifndef GH_ENC_LEAN_COPY
 #define GH_ENC_LEAN_COPY(syms_per_chunk) ((syms_per_chunk) == 4)
 #endif
+// fused gather (short-code variant): the chunks are built once, before the scans, and kept in registers (their
+// lengths give the bit counts), instead of a length gather before the scans and a code gather after them
+#ifndef GH_ENC_FUSED
+#define GH_ENC_FUSED 0
+#endif
 #ifndef GH_ENC_LOOK_DEPTH
 #define GH_ENC_LOOK_DEPTH 1
 #endif
@@ -148,6 +153,18 @@ __device__ __forceinline__ void lut_entry(smem_addr_t lut_lane, u32 byte, u32& c
   }
 }
 
+// one 64-bit chunk of the short-code variant from four table entries (code << 16 | len, 1 << len): acc = acc * 2^len
+// + code on the FMA pipe (see the kernel); returns the chunk's bit length
+__device__ __forceinline__ u32 build_chunk4(const uint2& e0, const uint2& e1, const uint2& e2, const uint2& e3, u32& lo, u32& hi) {
+  const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
+  const u64 p2 = u64(a01) * e2.y;                                               // <= 48 bits
+  const u32 lo2 = u32(p2) + __umulhi(e2.x, 1u << 16), hi2 = u32(p2 >> 32);
+  const u64 p3 = u64(lo2) * e3.y;
+  lo = u32(p3) + __umulhi(e3.x, 1u << 16);
+  hi = hi2 * e3.y + u32(p3 >> 32);
+  return (e0.x + e1.x + e2.x + e3.x) & 0xffffu;
+}
+
 template <int kSymsPerChunk>
 __global__ void __launch_bounds__(kEncThreads, kEncBlocksPerSm)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
@@ -204,9 +221,27 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
     }
     u32 bits[kEncSubTiles];
     int end_sub = -1;  // the sub-tile in which this thread owns the last input byte (it carries the end mark)
+    constexpr bool kFused = GH_ENC_FUSED && kSymsPerChunk == 4;
+    u32 ch_lo[kFused ? kEncSubTiles : 1][4], ch_hi[kFused ? kEncSubTiles : 1][4], ch_len[kFused ? kEncSubTiles : 1];
 #pragma unroll
     for (int j = 0; j < kEncSubTiles; ++j) {
       u32 b = 0;
+      if (kFused) {
+        // missing symbols of the ragged last vector count as (code 0, length 0, 2^0)
+        const bool whole = cnt[j] == kEncBytesPerThread;  // all but the one ragged vector at the end of the input
+        auto entry = [&](int k) -> uint2 {
+          return (whole || k < cnt[j]) ? lds_v2(lut_lane, vec_byte(raw[j], k) * u32(Smem::kSymStride)) : make_uint2(0u, 1u);
+        };
+        u32 lens = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const u32 clen = build_chunk4(entry(4 * c), entry(4 * c + 1), entry(4 * c + 2), entry(4 * c + 3),
+                                        ch_lo[kFused ? j : 0][c], ch_hi[kFused ? j : 0][c]);
+          lens |= clen << (8 * c);  // <= 64 each
+          b += clen;
+        }
+        ch_len[kFused ? j : 0] = lens;
+      } else
 #ifdef GH_PROBE_NO_COUNT  // tuning probe (wrong output): no length gather
       b = 6u * u32(cnt[j]) + (raw[j].x & 1u);
       if (false)
@@ -310,6 +345,14 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       u32* stage = s_stage[buf];
       {
         u32 pos = pos0[j];
+        if (kFused) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const u32 clen = (ch_len[kFused ? j : 0] >> (8 * c)) & 0xffu;
+            if (clen) stage_bits(stage, pos, (u64(ch_hi[kFused ? j : 0][c]) << 32) | ch_lo[kFused ? j : 0][c], clen);
+            pos += clen;
+          }
+        } else
 #ifdef GH_PROBE_NO_PACK  // tuning probe (wrong output): no code gather, no concatenation, no staging
         if (false)
 #endif

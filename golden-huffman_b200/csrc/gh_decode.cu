@@ -1541,12 +1541,12 @@ static u32 choose_sub_bytes(u64 slice_bytes) {
   return u32(s);
 }
 
-static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream) {
+static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream, bool fine) {
   const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
   GH_LAUNCH(dec_tile_sum_kernel, tiles, kDecThreads, 0, stream, g, ws);
   GH_LAUNCH(dec_locate_eof_kernel, 1, kDecThreads, 0, stream, g, ws);
   GH_LAUNCH(dec_offsets_kernel, 1, kScanThreads, 0, stream, g, ws);
-  GH_LAUNCH(dec_sub_offsets_kernel, tiles, kDecThreads, 0, stream, g, ws);
+  if (fine) GH_LAUNCH(dec_sub_offsets_kernel, tiles, kDecThreads, 0, stream, g, ws);  // only the fine writer reads out_off
   int rc = check_launch();
   if (rc != GH_OK) return rc;
   GH_CUDA_TRY(cudaMemcpyAsync(h_ctl, ws.ctl, sizeof(DecControl), cudaMemcpyDeviceToHost, stream));
@@ -1629,7 +1629,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     GH_LAUNCH(dec_phase_finish_kernel, blocks, kDecThreads, 0, stream, g, ws, (const u32*)ws.work[0]);
     int rc = check_launch();
     if (rc != GH_OK) return rc;
-    rc = dec_finish(g, ws, &h_ctl, stream);
+    rc = dec_finish(g, ws, &h_ctl, stream, false);
     if (rc != GH_OK) return rc;
     if (result) {
       result->n_symbols = h_ctl.total;
@@ -1744,7 +1744,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     speculate = true;
   }
 
-  int rc = dec_finish(g, ws, &h_ctl, stream);
+  int rc = dec_finish(g, ws, &h_ctl, stream, fine);
   if (rc != GH_OK) return rc;
   if (result) {
     result->n_symbols = h_ctl.total;

@@ -48,3 +48,65 @@ def test_device_path_equals_oracle(emu, ctx, oracle, data):
     dde = aligned(n + 32)
     nd, _ = emu.decompress_device(ctx, dout.ctypes.data, nb, dde.ctypes.data, n + 32)
     assert nd == n and dde[:n].tobytes() == data
+
+
+def _equal_frequency_bytes():
+    """every byte value `reps` times (-> the 8/9-bit code whose decode goes through the phase walk), arranged as a
+    seeded shuffle with the 9-bit byte's occurrences optionally gathered into runs (long stretches of zero bits:
+    an "eight zero bits start here" event at every position of the run, most of them not codeword starts)"""
+    def build(t):
+        reps, seed, run_frac = t
+        rng = np.random.default_rng(seed)
+        x = rng.permutation(np.repeat(np.arange(256, dtype=np.uint8), reps))
+        if run_frac:
+            # move a fraction of byte 2's occurrences (the byte that pairs with the end mark: 9-bit code 000000000) together
+            idx = np.flatnonzero(x == 2)
+            k = max(1, int(len(idx) * run_frac / 4))
+            others = np.flatnonzero(x != 2)[:k]
+            x[idx[:k]], x[others] = x[others].copy(), x[idx[:k]].copy()
+            x = np.concatenate([x[x == 2][:k], x[~np.isin(np.arange(len(x)), np.flatnonzero(x == 2)[:k])]])
+        return x.tobytes()
+    return st.tuples(st.integers(20, 60), st.integers(0, 2**31), st.sampled_from([0, 1, 2, 4])).map(build)
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(data=_equal_frequency_bytes(), cut_frac=st.floats(0.2, 0.8))
+def test_phase_walk_equals_oracle(emu, ctx, oracle, data, cut_frac):
+    """whole-image round trip, and the payload decoded as two shards with the second one's entry corrected"""
+    import golden_huffman_b200 as gh
+    n = len(data)
+    rc, code = oracle.build_code(oracle.histogram(data))
+    if not (code.min_len == 8 and code.max_len == 9):
+        return  # the arrangement does not change the histogram, so this cannot happen; guard anyway
+    din = aligned(n + 16)
+    din[:n] = np.frombuffer(data, dtype=np.uint8)
+    rc, img = oracle.compress(data)
+    cap = emu.compress_bound(n)
+    dout = aligned(cap)
+    nb, _ = emu.compress_device(ctx, din.ctypes.data, n, dout.ctypes.data, cap)
+    assert dout[:nb].tobytes() == img
+    dde = aligned(n + 32)
+    nd, _ = emu.decompress_device(ctx, dout.ctypes.data, nb, dde.ctypes.data, n + 32)
+    assert nd == n and dde[:n].tobytes() == data
+    # two shards
+    _, payload = oracle.encode_payload(data, code)
+    pcode = gh.GhCode.from_buffer_copy(bytes(code))
+    cut = max(4096, int(len(payload) * cut_frac)) // 16 * 16
+    if len(payload) - cut < 4096:
+        return
+    buf = aligned(len(payload) + 16)
+    buf[:len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+    slices = [(0, cut, min(cut + 8, len(payload))), (cut, len(payload) - cut, len(payload) - cut)]
+    ws = [aligned(emu.decode_workspace_bytes(s[1]) + 256) for s in slices]
+    res = [emu.decode_sync(buf.ctypes.data + off, nb_, rd, pcode, 0, True, ws[k].ctypes.data, ws[k].size)
+           for k, (off, nb_, rd) in enumerate(slices)]
+    res[1] = emu.decode_sync(buf.ctypes.data + cut, slices[1][1], slices[1][2], pcode, res[0].exit_bit, False,
+                             ws[1].ctypes.data, ws[1].size)
+    assert res[1].eof_found and res[0].n_symbols + res[1].n_symbols == n
+    out = aligned(n + 16)
+    o = 0
+    for k, (off, nb_, rd) in enumerate(slices):
+        emu.decode_write(buf.ctypes.data + off, nb_, rd, pcode, out.ctypes.data + o, res[k].n_symbols,
+                         ws[k].ctypes.data, ws[k].size)
+        o += res[k].n_symbols
+    assert out[:n].tobytes() == data

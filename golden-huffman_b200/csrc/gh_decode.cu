@@ -20,9 +20,14 @@
 //                    each touching fewer subsequences.
 //   K6   offsets   : the first end mark on the synchronised path truncates the counts (one thread walks that one
 //                    subsequence to count the symbols before it); exclusive scan -> output offsets.
-//   K7   write     : every thread re-decodes its subsequence from its now-exact entry, up to 3 codewords per
-//                    13-bit table lookup (long codes: left-justified first_code search, as the reference's Fast
+//                    Codes that need about a whole subsequence to re-synchronise take re-walk rounds over
+//                    dense work lists instead (dec_worklist_kernel), and the 8/9-bit code of equally frequent
+//                    bytes takes no rounds at all: K5c, the phase walk (transfer functions composed by a scan).
+//   K7   write     : every thread re-decodes its subsequence from its now-exact entry, up to 2 codewords per
+//                    12-bit table lookup (long codes: left-justified first_code search, as the reference's Fast
 //                    decoder does), and stores symbols 16 at a time with 128-bit stores.
+// K5a and K7 share the "cursor reader" (below): table entries are addends for one cursor word, lanes read their
+// subsequences in 32-byte units (one sector per lane and request) in a word-synchronous loop.
 // The lookup tables are expanded from the header's canonical tables by a kernel (dec_build_luts_kernel).
 //
 // Algorithmic traffic: C bytes read + N bytes written; this implementation reads the payload twice

@@ -7,15 +7,17 @@
 //
 // Persistent blocks take tiles of kEncSubTiles x 4 KiB of input from an atomic ticket. Per tile:
 //   1. every thread issues kEncSubTiles coalesced 128-bit loads up front (one 16-byte vector per 4 KiB sub-tile,
-//      kept in registers) and sums the code lengths of its bytes from the shared-memory LUT;
+//      kept in registers) and sums the code lengths of its bytes from the shared-memory LUT, which is replicated
+//      across the banks so that the gathers are (nearly) conflict-free (see EncSmem);
 //   2. the per-thread bit counts are scanned per sub-tile (warp shuffles + one barrier); warp 0 publishes the
 //      tile total and resolves the tile's global bit offset G by a warp-wide decoupled look-back over the
 //      predecessors' (flag | value) words. One look-back per 16 KiB: the prefix can only travel 32 tiles per
 //      L2 round trip, so with 4 KiB tiles that chain, not the SMs, set the pace (measured: profiles/r1b);
 //   3. sub-tile by sub-tile: codewords are concatenated in registers into 64-bit chunks (4 per chunk when no
-//      code is longer than 16 bits, else 2) -- `acc = (acc << len) | code` -- and OR-ed into a zeroed shared
-//      staging buffer at sub-tile-relative bit positions (shared-memory atomics: neighbours share words).
-//      Packing needs no global offset, so the other warps pack while warp 0 is still looking back;
+//      code is longer than 16 bits -- by multiply-adds with 2^len from the table --, else 2 by shifts) and OR-ed
+//      into a zeroed shared staging buffer at sub-tile-relative bit positions (shared-memory atomics: neighbours
+//      share words). Packing needs no global offset, so the other warps pack while warp 0 is still looking back.
+//      The short-code variant rotates three staging buffers and needs one barrier per sub-tile;
 //   4. copy-out: global word (G'/32 + i) = funnel-shift of staged words i-1, i by (G' mod 32), G' the sub-tile's
 //      global bit offset -- phase alignment costs one SHF per output word -- byte-swapped to stream order,
 //      coalesced. A sub-tile's trailing partial word is carried (shared memory) into the next sub-tile's first

@@ -1710,7 +1710,11 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
                     (const u32*)ws.work[cur], work_n, ws.work[cur ^ 1]);
         }
       } else {
-        GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
+        // Re-entry with a corrected first-codeword position (sharded decode): everything but subsequence 0 was at
+        // the fixed point, and staleness only travels rightwards through exits that move, so the first round needs
+        // the first block only; a moved exit at its end sets `changed` and the following rounds are full ones.
+        const unsigned sync_blocks = (!first_call && !speculate && level_round == 0) ? 1u : blocks;
+        GH_LAUNCH(dec_sync_kernel, sync_blocks, kDecThreads, 0, stream, g, ws);
         have_list = false;
       }
       rc = check_launch();

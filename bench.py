@@ -293,6 +293,7 @@ def main():
             "dec_build_luts_kernel": 0, "dec_speculate_kernel": C_, "dec_sync_kernel": 0, "dec_tile_sum_kernel": 0, "dec_offsets_kernel": 0,
             "dec_write_kernel": C_ + n, "dec_fine_speculate_kernel": C_, "dec_fine_write_kernel": C_ + n,
             "dec_sub_offsets_kernel": 0, "dec_locate_eof_kernel": 0,
+            "dec_phase_walk_kernel": C_, "dec_worklist_kernel": 0,  # K5c reads the payload once, like K5a
         }
         def alg_bytes(name):
             return alg.get(name.split("<")[0], 0)

@@ -25,6 +25,8 @@
 //      head[tile] and a tiny second kernel ORs them into the word the previous tile wrote -- every output
 //      word has exactly one writer per kernel, no global atomics on the payload. The last tile adds the
 //      end-mark codeword and the 1-padding (reference include/canonical_huff_encoder.cc:255-257).
+#include <stdlib.h>
+
 #include "gh_common.cuh"
 
 namespace gh {
@@ -133,6 +135,61 @@ __device__ __forceinline__ void stage_bits(u32* stage, u32 pos, u64 acc, u32 len
 __device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
   const u32 w = (k >> 2) == 0 ? v.x : (k >> 2) == 1 ? v.y : (k >> 2) == 2 ? v.z : v.w;
   return __byte_perm(w, 0u, 0x4440u | u32(k & 3));
+}
+
+// Decoupled look-back (Merrill & Garland) by one whole warp: publishes this tile's bit count, adds up the
+// predecessors' counts back to the nearest tile that already knows its start, publishes this tile's end bit and
+// returns its start bit (all 32 lanes must call it together).
+__device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 tile, u32 tile_bits, u64 start_bit, unsigned lane) {
+  u64 exclusive = start_bit;
+  if (tile == 0) {
+    if (lane == 0) st_volatile_u64(ws.tile_state, kFlagPrefix | (start_bit + tile_bits));
+  } else {
+    if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
+    exclusive = 0;
+    long long look = (long long)tile - 1;
+    bool done = false;
+#ifdef GH_PROBE_NO_LOOKBACK  // tuning probe (wrong output): pretend every tile is 6 bits per byte
+    exclusive = start_bit + tile * u64(kEncTileBytes) * 6;
+    done = true;
+#endif
+    while (!done) {
+      // One round trip covers 32 x kEncLookDepth predecessors: lane l owns the kEncLookDepth consecutive tiles
+      // look - l * kEncLookDepth - r (r = 0 nearest), loads all of them at once, folds them locally (sum of
+      // aggregates up to and including its nearest PREFIX) and the warp then needs ONE ballot + ONE sum.
+      // The kernel's throughput is capped at (tiles covered per round) / (round time): tiles that cannot find
+      // a prefix in a round queue up behind those that can, so the window per round is what has to be wide.
+      const long long first_idx = look - (long long)lane * kEncLookDepth;
+      u64 st[kEncLookDepth];
+#pragma unroll
+      for (int r = 0; r < kEncLookDepth; ++r) {
+        const long long idx = first_idx - r;
+        st[r] = idx >= 0 ? ld_volatile_u64(ws.tile_state + idx) : kFlagPrefix;  // virtual tiles before tile 0 add nothing
+      }
+      u64 local = 0;
+      bool local_prefix = false;
+#pragma unroll
+      for (int r = 0; r < kEncLookDepth; ++r) {
+        const long long idx = first_idx - r;
+        while ((st[r] & kFlagMask) == 0) {  // not published yet
+          if (kEncPollSleepNs) __nanosleep(kEncPollSleepNs);
+          st[r] = ld_volatile_u64(ws.tile_state + idx);
+        }
+        if (!local_prefix) local += st[r] & ~kFlagMask;
+        local_prefix = local_prefix || (st[r] & kFlagMask) == kFlagPrefix;
+      }
+      const unsigned has_prefix = __ballot_sync(0xffffffffu, local_prefix);
+      // lanes up to and including the nearest one that found a prefix contribute
+      const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
+      const u64 contrib = (has_prefix == 0 || lane <= first) ? local : 0ull;
+      exclusive += warp_sum64(contrib);
+      done = has_prefix != 0;
+      look -= 32 * kEncLookDepth;
+    }
+    if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
+  }
+  return exclusive;
+
 }
 
 // gather from this lane's copy of the table (see EncSmem)
@@ -290,53 +347,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
     }
 
     if (warp == 0) {
-      u64 exclusive = start_bit;
-      if (tile == 0) {
-        if (lane == 0) st_volatile_u64(ws.tile_state, kFlagPrefix | (start_bit + tile_bits));
-      } else {
-        if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
-        exclusive = 0;
-        long long look = (long long)tile - 1;
-        bool done = false;
-#ifdef GH_PROBE_NO_LOOKBACK  // tuning probe (wrong output): pretend every tile is 6 bits per byte
-        exclusive = start_bit + tile * u64(kEncTileBytes) * 6;
-        done = true;
-#endif
-        while (!done) {
-          // One round trip covers 32 x kEncLookDepth predecessors: lane l owns the kEncLookDepth consecutive tiles
-          // look - l * kEncLookDepth - r (r = 0 nearest), loads all of them at once, folds them locally (sum of
-          // aggregates up to and including its nearest PREFIX) and the warp then needs ONE ballot + ONE sum.
-          // The kernel's throughput is capped at (tiles covered per round) / (round time): tiles that cannot find
-          // a prefix in a round queue up behind those that can, so the window per round is what has to be wide.
-          const long long first_idx = look - (long long)lane * kEncLookDepth;
-          u64 st[kEncLookDepth];
-#pragma unroll
-          for (int r = 0; r < kEncLookDepth; ++r) {
-            const long long idx = first_idx - r;
-            st[r] = idx >= 0 ? ld_volatile_u64(ws.tile_state + idx) : kFlagPrefix;  // virtual tiles before tile 0 add nothing
-          }
-          u64 local = 0;
-          bool local_prefix = false;
-#pragma unroll
-          for (int r = 0; r < kEncLookDepth; ++r) {
-            const long long idx = first_idx - r;
-            while ((st[r] & kFlagMask) == 0) {  // not published yet
-              if (kEncPollSleepNs) __nanosleep(kEncPollSleepNs);
-              st[r] = ld_volatile_u64(ws.tile_state + idx);
-            }
-            if (!local_prefix) local += st[r] & ~kFlagMask;
-            local_prefix = local_prefix || (st[r] & kFlagMask) == kFlagPrefix;
-          }
-          const unsigned has_prefix = __ballot_sync(0xffffffffu, local_prefix);
-          // lanes up to and including the nearest one that found a prefix contribute
-          const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
-          const u64 contrib = (has_prefix == 0 || lane <= first) ? local : 0ull;
-          exclusive += warp_sum64(contrib);
-          done = has_prefix != 0;
-          look -= 32 * kEncLookDepth;
-        }
-        if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
-      }
+      const u64 exclusive = tile_start_lookback(ws, tile, tile_bits, start_bit, lane);
       if (lane == 0) s_tile_start = exclusive;
     }
 
@@ -467,6 +478,206 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   }
 }
 
+// ---- experimental: encoder with warp-independent phases (short codes only, GH_ENCODE_KERNEL=warp) -----------------
+// The probe builds (tools/enc_probe.py) show that the phases of encode_kernel add up: its barrier-separated phases
+// overlap too little. Here every warp owns a 2 KiB slice of the tile (kEncSubTiles rows of 32 lanes x 16 bytes) and a
+// staging area of its own, so that between the block-wide barriers the warps run their phases independently:
+//   count + warp scans -> barrier 1 (the eight warp totals) -> warp 0 looks back while every warp packs all its rows
+//   at warp-relative positions -> barrier 2 (the tile's start bit) -> every warp copies its own range out with its own
+//   phase; the first / last word of a warp's range, when shared with a neighbour, goes to a small edge array ->
+//   barrier 3 -> one thread merges the edges (and hands the tile's shared first word to head[], as encode_kernel does).
+// Same output, same workspace protocol (tile_state, head[], encode_stitch_kernel). NOT MEASURED YET on a B200 (written
+// after this round's GPU budget was spent); bit-exact under tests/emul. Not the default.
+#ifndef GH_ENC_WARP_BLOCKS
+#define GH_ENC_WARP_BLOCKS 4
+#endif
+struct EncWarpSmem {
+  static constexpr int kWarps = kEncThreads / 32;
+  static constexpr int kRows = kEncSubTiles;
+  static constexpr int kWarpBytes = kRows * 32 * kEncBytesPerThread;  // 2 KiB
+  static constexpr int kStageWords = (kWarpBytes * 16 + 32 + 31) / 32 + 2;
+  static constexpr int kCopies = 8;
+  static constexpr int kSymStride = kCopies * 8;
+  u32 lut[256 * kCopies * 2];
+  u32 stage[kWarps][kStageWords];
+  u32 wtot[kWarps];
+  u64 edge_word[kWarps][2];
+  u32 edge_val[kWarps][2];
+  u32 edge_n[kWarps];
+  u32 tile;
+  u64 tile_start;
+};
+static_assert(EncWarpSmem::kWarps * EncWarpSmem::kWarpBytes == kEncTileBytes, "a tile is one slice per warp");
+
+__global__ void __launch_bounds__(kEncThreads, GH_ENC_WARP_BLOCKS)
+encode_warp_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
+                   u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
+  typedef EncWarpSmem Smem;
+  GH_DYNAMIC_SMEM(smem_raw);
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) sm.tile = atomicAdd(ws.ticket, 1u);
+  for (unsigned i = t; i < 256u * Smem::kCopies; i += kEncThreads) {
+    const unsigned sym = i / Smem::kCopies;
+    sm.lut[2 * i] = (table.codeword[sym] << 16) | table.length[sym];
+    sm.lut[2 * i + 1] = 1u << table.length[sym];
+  }
+  for (unsigned i = t; i < unsigned(Smem::kWarps) * Smem::kStageWords; i += kEncThreads) (&sm.stage[0][0])[i] = 0;
+  __syncthreads();
+  const smem_addr_t lut_lane = smem_addr(sm.lut) + (lane & u32(Smem::kCopies - 1)) * 8u;
+  u32* const stage = sm.stage[warp];
+  const u64 ntiles = enc_num_tiles(n);
+  const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
+  const u32 eof_len = table.length[GH_EOF_SYMBOL];
+
+  for (u64 tile = sm.tile; tile < ntiles; tile = sm.tile) {
+    const bool last_tile = (tile + 1 == ntiles);
+    // ---- 1. loads and bit counts of this lane's kRows vectors -----------------------------------------------
+    uint4 raw[Smem::kRows];
+    int cnt[Smem::kRows];
+    u32 bits[Smem::kRows];
+    int end_row = -1;  // the row in which this lane owns the last input byte (it carries the end mark)
+#pragma unroll
+    for (int r = 0; r < Smem::kRows; ++r) {
+      const u64 base = tile * kEncTileBytes + u64(warp) * Smem::kWarpBytes + u64(r) * (32 * kEncBytesPerThread) +
+                       u64(lane) * kEncBytesPerThread;
+      raw[r] = make_uint4(0, 0, 0, 0);
+      cnt[r] = 0;
+      if (base + kEncBytesPerThread <= n) {
+        raw[r] = ldg128(reinterpret_cast<const uint4*>(in + base));
+        cnt[r] = kEncBytesPerThread;
+      } else if (base < n) {
+        cnt[r] = int(n - base);
+        raw[r] = load_ragged(in + base, cnt[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < Smem::kRows; ++r) {
+      u32 b = 0;
+      if (cnt[r] == kEncBytesPerThread) {
+#pragma unroll
+        for (int k = 0; k < kEncBytesPerThread; ++k) b += lds_u32(lut_lane, vec_byte(raw[r], k) * u32(Smem::kSymStride));
+      } else {
+        for (int k = 0; k < cnt[r]; ++k) b += lds_u32(lut_lane, vec_byte(raw[r], k) * u32(Smem::kSymStride));
+      }
+      b &= 0xffffu;  // whole entries were summed: the lengths are their low halves
+      const u64 base = tile * kEncTileBytes + u64(warp) * Smem::kWarpBytes + u64(r) * (32 * kEncBytesPerThread) +
+                       u64(lane) * kEncBytesPerThread;
+      if (append_eof && last_tile && base < n && base + kEncBytesPerThread >= n) {
+        end_row = r;
+        b += eof_len;
+      }
+      bits[r] = b;
+    }
+    // ---- 2. warp-relative positions; the warp totals are all the block has to exchange -----------------------
+    u32 pos[Smem::kRows];
+    u32 wbits = 0;
+#pragma unroll
+    for (int r = 0; r < Smem::kRows; ++r) {
+      const u32 incl = warp_inclusive_scan(bits[r], lane);
+      pos[r] = wbits + incl - bits[r];
+      wbits += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) sm.wtot[warp] = wbits;
+    __syncthreads();  // (1)
+    u32 woff = 0, tile_bits = 0;
+#pragma unroll
+    for (int k = 0; k < Smem::kWarps; ++k) {
+      const u32 v = sm.wtot[k];
+      if (unsigned(k) < warp) woff += v;
+      tile_bits += v;
+    }
+    if (warp == 0) {
+      const u64 exclusive = tile_start_lookback(ws, tile, tile_bits, start_bit, lane);
+      if (lane == 0) sm.tile_start = exclusive;
+    }
+    // ---- 3. pack all rows into the warp's own staging area ---------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < Smem::kRows; ++r) {
+      u32 p = pos[r];
+      if (cnt[r] == kEncBytesPerThread) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          u32 lo, hi;
+          const u32 clen = build_chunk4(lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 0) * u32(Smem::kSymStride)),
+                                        lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 1) * u32(Smem::kSymStride)),
+                                        lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 2) * u32(Smem::kSymStride)),
+                                        lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 3) * u32(Smem::kSymStride)), lo, hi);
+          stage_bits(stage, p, (u64(hi) << 32) | lo, clen);
+          p += clen;
+        }
+      } else {  // the ragged last vector of the input: symbol by symbol
+        for (int k = 0; k < cnt[r]; ++k) {
+          const u32 e = lds_u32(lut_lane, vec_byte(raw[r], k) * u32(Smem::kSymStride));
+          stage_bits(stage, p, e >> 16, e & 0xffffu);
+          p += e & 0xffffu;
+        }
+      }
+      if (end_row == r && eof_len) stage_bits(stage, p, eof_code, eof_len);
+    }
+    __syncthreads();  // (2) staging complete, tile start known
+    if (t == 0) sm.tile = atomicAdd(ws.ticket, 1u);  // next tile (read after barrier 3)
+    // ---- 4. copy-out of this warp's range --------------------------------------------------------------------
+    const u64 tile_G = sm.tile_start;
+    const u64 G = tile_G + woff;
+    const u32 nbits = wbits;
+    const u32 phase = u32(G & 31);
+    const u64 end_bit = G + nbits;
+    const bool stream_end = last_tile && nbits && (woff + nbits == tile_bits);  // no bits follow in the whole stream
+    u32 pad = 0;
+    if (append_eof && stream_end) pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s to the byte
+    if (stream_end && lane == 0 && end_bit_out) *end_bit_out = end_bit;
+    const u32 padmask = pad ? ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad)) : 0u;
+    const u64 word0 = G >> 5;
+    const u32 nwords = nbits ? u32((u64(phase) + nbits + pad + 31) >> 5) : 0u;
+    const bool head_partial = nwords && phase != 0;
+    const bool tail_partial = nwords && ((phase + nbits + pad) & 31) != 0 && !(nwords == 1 && head_partial);
+    const u32 lo_i = head_partial ? 1u : 0u, hi_i = nwords - (tail_partial ? 1u : 0u);
+    auto word_at = [&](u32 i) -> u32 {
+      u32 v = __funnelshift_r(stage[i], i ? stage[i - 1] : 0u, phase);
+      if (i == nwords - 1) v |= padmask;
+      return v;
+    };
+    for (u32 i = lo_i + lane; i < hi_i; i += 32) {
+      if (word0 + i < out_word_cap) out_words[word0 + i] = be32(word_at(i));
+    }
+    if (lane == 0) {  // words this warp shares with its neighbours
+      u32 ne = 0;
+      if (head_partial) sm.edge_word[warp][ne] = word0, sm.edge_val[warp][ne] = word_at(0), ++ne;
+      if (tail_partial) sm.edge_word[warp][ne] = word0 + nwords - 1, sm.edge_val[warp][ne] = word_at(nwords - 1), ++ne;
+      sm.edge_n[warp] = ne;
+    }
+    __syncwarp();
+    for (u32 i = lane; i < (nbits >> 5) + 3; i += 32) stage[i] = 0;  // clean for the next tile
+    __syncthreads();  // (3) edges written
+    if (t == 0) {
+      // contributions in stream order; equal word indices are merged; the tile's first word, when shared with the
+      // previous tile, goes to head[] (encode_stitch_kernel ORs it into what that tile stored)
+      const bool shared_head = tile > 0 && (tile_G & 31) != 0;
+      const u64 tile_word0 = tile_G >> 5;
+      u64 cur_word = ~0ull;
+      u32 cur_val = 0;
+      for (int w = 0; w <= Smem::kWarps; ++w) {
+        const u32 ne = w < Smem::kWarps ? sm.edge_n[w] : 1u;
+        for (u32 k = 0; k < ne; ++k) {
+          const u64 wd = w < Smem::kWarps ? sm.edge_word[w][k] : ~0ull;  // the extra round flushes the last word
+          const u32 v = w < Smem::kWarps ? sm.edge_val[w][k] : 0u;
+          if (wd != cur_word) {
+            if (cur_word != ~0ull) {
+              if (shared_head && cur_word == tile_word0) ws.head[tile] = cur_val;
+              else if (cur_word < out_word_cap) out_words[cur_word] = be32(cur_val);
+            }
+            cur_word = wd;
+            cur_val = v;
+          } else {
+            cur_val |= v;
+          }
+        }
+      }
+    }
+  }
+}
+
 // Second kernel: OR each tile's deferred head bits into the word its predecessor stored.
 // Thread = tile. The first tile (in order) holding head bits for a given word merges the whole run.
 __global__ void __launch_bounds__(256)
@@ -562,7 +773,23 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   if (per_sm < 1) per_sm = kEncBlocksPerSm;
   u64 blocks = u64(sm_count() > 0 ? sm_count() : 1) * u64(per_sm);
   if (blocks > ntiles) blocks = ntiles;
-  if (short_codes) {
+  const char* which = getenv("GH_ENCODE_KERNEL");
+  if (short_codes && which && which[0] == 'w') {  // experimental warp-independent kernel, see encode_warp_kernel
+    static bool warp_attr = false;
+    if (!warp_attr) {
+      GH_CUDA_TRY(cudaFuncSetAttribute(encode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(EncWarpSmem))));
+      warp_attr = true;
+    }
+    int wp = 0;
+#ifndef GH_EMUL
+    GH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wp, encode_warp_kernel, kEncThreads, sizeof(EncWarpSmem)));
+#endif
+    if (wp < 1) wp = GH_ENC_WARP_BLOCKS;
+    u64 wblocks = u64(sm_count() > 0 ? sm_count() : 1) * u64(wp);
+    if (wblocks > ntiles) wblocks = ntiles;
+    GH_LAUNCH(encode_warp_kernel, unsigned(wblocks), kEncThreads, sizeof(EncWarpSmem), stream, d_in, (u64)n, table, (u64)start_bit,
+              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
+  } else if (short_codes) {
     GH_LAUNCH(encode_kernel<4>, unsigned(blocks), kEncThreads, sizeof(EncSmem<4>), stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
               reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
   } else {

@@ -63,6 +63,43 @@ def test_emulated_near_fixed_length_code(emu, ctx, oracle):
     _roundtrip(emu, ctx, oracle, np.repeat(np.arange(256, dtype=np.uint8), 300).tobytes())
 
 
+def test_emulated_warp_independent_encoder(emu, ctx, oracle, monkeypatch):
+    """GH_ENCODE_KERNEL=warp selects the experimental encoder whose warps run their phases independently (short codes
+    only; long codes keep the default kernel): same bytes as the oracle on the golden inputs, on ragged sizes and
+    with every start phase of the sharding contract"""
+    import golden_huffman_b200 as gh
+    monkeypatch.setenv("GH_ENCODE_KERNEL", "warp")
+    for name in ["kat1_abracadabra", "kat2_a1000", "one_byte", "two_symbols", "text_small", "tile_exact_4096",
+                 "tile_plus1_4097", "kat3_allbytes512"]:
+        _roundtrip(emu, ctx, oracle, make_input(name))
+    rng = np.random.default_rng(17)
+    for n in (5, 511, 2049, 16384, 16385, 40000):
+        _roundtrip(emu, ctx, oracle, np.minimum(rng.geometric(0.3, n), 255).astype(np.uint8).tobytes())
+    data = make_input("text_small")
+    n = len(data)
+    rc, code = oracle.build_code(oracle.histogram(data))
+    _, full = oracle.encode_payload(data, code)
+    bits = np.unpackbits(np.frombuffer(full, dtype=np.uint8))
+    total = oracle.payload_bits(code, oracle.histogram(data)) - code.length[256]
+    pcode = gh.GhCode.from_buffer_copy(bytes(code))
+    for start_bit in (0, 5, 31, 32, 77, 127, 255):
+        din = aligned(n + 16)
+        din[:n] = np.frombuffer(data, dtype=np.uint8)
+        cap = emu.encode_payload_capacity(n, pcode, start_bit)
+        out = aligned(cap)
+        out[:] = 0xAA
+        ws = aligned(emu.encode_workspace_bytes(n) + 256)
+        end = aligned(1, np.uint64)
+        emu.encode(din.ctypes.data, n, pcode, out.ctypes.data, cap, ws.ctypes.data, ws.size, start_bit=start_bit,
+                   append_eof=False, d_end_bit=end.ctypes.data)
+        assert int(end[0]) == start_bit + total
+        first_word = start_bit // 32 * 4
+        got = np.unpackbits(out[first_word:])
+        lead = start_bit - first_word * 8
+        assert not got[:lead].any()
+        assert (got[lead:lead + total] == bits[:total]).all()
+
+
 def test_emulated_kernels_random(emu, ctx, oracle):
     rng = np.random.default_rng(3)
     sizes = [3, 17, 4095, 8193, 30000]

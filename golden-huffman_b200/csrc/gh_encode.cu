@@ -486,8 +486,9 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
 //   at warp-relative positions -> barrier 2 (the tile's start bit) -> every warp copies its own range out with its own
 //   phase; the first / last word of a warp's range, when shared with a neighbour, goes to a small edge array ->
 //   barrier 3 -> one thread merges the edges (and hands the tile's shared first word to head[], as encode_kernel does).
-// Same output, same workspace protocol (tile_state, head[], encode_stitch_kernel). NOT MEASURED YET on a B200 (written
-// after this round's GPU budget was spent); bit-exact under tests/emul. Not the default.
+// Same output, same workspace protocol (tile_state, head[], encode_stitch_kernel). Measured once (r3i, tools/
+// enc_warp_check.py): bit-identical to encode_kernel on the B200 and 1.71 ms vs 1.67 ms for 1 GiB Zipf at 4 blocks per
+// SM -- no gain as it stands, so it is not the default; kept as the starting point for the next round's experiments.
 #ifndef GH_ENC_WARP_BLOCKS
 #define GH_ENC_WARP_BLOCKS 4
 #endif

@@ -12,7 +12,7 @@ import golden_huffman_b200 as gh  # noqa: E402
 import golden_huffman_b200.workloads as W  # noqa: E402
 
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-codec = gh.Codec(gh.GhLib())
+codec = gh.Codec(gh.GhLib(os.environ.get("GH_LIB_PATH") or None))
 for wl, n in (("zipf", (1 << 20) * mib), ("uniform", (1 << 24) + 12345), ("zipf", 70001), ("zipf", 16384)):
     x = {"zipf": W.zipf_torch, "uniform": W.uniform_torch}[wl](n, torch.device("cuda"))
     code = codec.build_code(codec.histogram(x))

@@ -3,94 +3,71 @@
 // per-bit writer utils/include/buffer.h:241-248,277-295).
 //
 // Algorithmic traffic: N bytes read + C bytes written (the scan is fused by decoupled look-back, so the
-// input is not read a second time to learn the bit offsets).
+// input is not read a second time to learn the bit offsets, and every input byte is looked up ONCE).
 //
-// Persistent blocks take tiles of kEncSubTiles x 4 KiB of input from an atomic ticket. Per tile:
-//   1. every thread issues kEncSubTiles coalesced 128-bit loads up front (one 16-byte vector per 4 KiB sub-tile,
-//      kept in registers) and sums the code lengths of its bytes from the shared-memory LUT, which is replicated
-//      across the banks so that the gathers are (nearly) conflict-free (see EncSmem);
-//   2. the per-thread bit counts are scanned per sub-tile (warp shuffles + one barrier); warp 0 publishes the
-//      tile total and resolves the tile's global bit offset G by a warp-wide decoupled look-back over the
-//      predecessors' (flag | value) words. One look-back per 16 KiB: the prefix can only travel 32 tiles per
-//      L2 round trip, so with 4 KiB tiles that chain, not the SMs, set the pace (measured: profiles/r1b);
-//   3. sub-tile by sub-tile: codewords are concatenated in registers into 64-bit chunks (4 per chunk when no
-//      code is longer than 16 bits -- by multiply-adds with 2^len from the table --, else 2 by shifts) and OR-ed
-//      into a zeroed shared staging buffer at sub-tile-relative bit positions (shared-memory atomics: neighbours
-//      share words). Packing needs no global offset, so the other warps pack while warp 0 is still looking back.
-//      The short-code variant rotates three staging buffers and needs one barrier per sub-tile;
-//   4. copy-out: global word (G'/32 + i) = funnel-shift of staged words i-1, i by (G' mod 32), G' the sub-tile's
-//      global bit offset -- phase alignment costs one SHF per output word -- byte-swapped to stream order,
-//      coalesced. A sub-tile's trailing partial word is carried (shared memory) into the next sub-tile's first
-//      word. The tile's first word, when shared with the previous tile, is NOT stored: its bits go to
-//      head[tile] and a tiny second kernel ORs them into the word the previous tile wrote -- every output
-//      word has exactly one writer per kernel, no global atomics on the payload. The last tile adds the
-//      end-mark codeword and the 1-padding (reference include/canonical_huff_encoder.cc:255-257).
-#include <stdlib.h>
-
+// One persistent CTA of 1024 threads per SM, split into four independent GROUPS of 256 threads that share one
+// lookup table and synchronise among themselves with named barriers only. A group takes TILES of input from an
+// atomic ticket; a tile is kSubTiles sub-tiles of 8 KiB, a thread owns 32 consecutive bytes of a sub-tile.
+//   1. gather + concatenate: per byte one PRMT (which forms the complete shared-memory address: the table has one
+//      64-bit entry (code << 16 | len, 2^len) per (byte value, lane) at 0x10000 + value * 256 + lane * 8, so the
+//      gathers of a warp can never conflict) and one LDS.64; four codewords are concatenated into a 64-bit chunk by
+//      multiply-adds with the powers of two (FMA pipe), the chunk length is the sum of the entries' low halves;
+//   2. per sub-tile: warp-shuffle scan of the thread bit counts, the eight warp totals cross one named barrier;
+//   3. staging: every chunk is OR-ed into the group's zeroed staging buffer at its TILE-relative bit position with
+//      shared-memory atomics (neighbouring chunks share words). This needs no global offset, so it runs before
+//      the tile's look-back has finished;
+//   4. the tile's bit count is published as (AGGREGATE | bits) as soon as the last sub-tile is counted; after
+//      staging, the group's first warp resolves the tile's start bit G by a decoupled look-back (Merrill & Garland)
+//      over 96 predecessors per L2 round trip -- with 32 per round trip the chain of prefixes, not the SMs, bounds a
+//      kernel this fast (16 KiB x 32 / 0.37 us = 1.4 TB/s) -- and publishes (PREFIX | end bit);
+//   5. copy-out: global word (G/32 + i) = funnel shift of staged words i-1, i by (G mod 32), byte-swapped to
+//      stream order, coalesced. The tile's first word, when shared with the previous tile, is NOT stored: its
+//      bits go to head[tile] and encode_stitch_kernel ORs them into the word the previous tile wrote -- every
+//      output word has exactly one writer per kernel, no global atomics on the payload. The last tile adds the
+//      1-padding (reference include/canonical_huff_encoder.cc:255-257); the staging buffer is cleared again.
+// Codewords longer than 16 bits cannot take part in step 1 (four of them do not fit a 64-bit chunk). Their table
+// entries carry a flag that survives the length sum; a warp whose 1 KiB slice of the sub-tile contains one -- or the
+// ragged end of the input, or the byte that the end mark follows -- handles that slice codeword by codeword
+// (count_slow / stage_slow). A Huffman code gives such lengths only to symbols rarer than 2^-16 or so.
+// When the code has such codewords, tiles are one sub-tile (8 KiB), so that even a tile of nothing but 32-bit
+// codewords fits the staging buffer.
 #include "gh_common.cuh"
 
 namespace gh {
 
-constexpr int kEncThreads = 256;
-constexpr int kEncBytesPerThread = 16;
-constexpr int kEncSubTileBytes = kEncThreads * kEncBytesPerThread;  // 4 KiB
-#ifndef GH_ENC_SUBTILES
-#define GH_ENC_SUBTILES 4
-#endif
-#ifndef GH_ENC_BLOCKS_PER_SM
-#define GH_ENC_BLOCKS_PER_SM 5
-#endif
-constexpr int kEncSubTiles = GH_ENC_SUBTILES;
-constexpr int kEncTileBytes = kEncSubTileBytes * kEncSubTiles;      // 16 KiB per look-back
-constexpr int kEncBlocksPerSm = GH_ENC_BLOCKS_PER_SM;
-// lean interior copy-out loop: for which variants (measured r3b: helps the short-code variant, not the long-code one)
-#ifndef GH_ENC_LEAN_COPY
-#define GH_ENC_LEAN_COPY(syms_per_chunk) ((syms_per_chunk) == 4)
-#endif
-// fused gather (short-code variant): the chunks are built once, before the scans, and kept in registers (their
-// lengths give the bit counts), instead of a length gather before the scans and a code gather after them
-#ifndef GH_ENC_FUSED
-#define GH_ENC_FUSED 0
-#endif
-#ifndef GH_ENC_LOOK_DEPTH
-#define GH_ENC_LOOK_DEPTH 1
-#endif
-#ifndef GH_ENC_TICKET_SUBTILE
-#define GH_ENC_TICKET_SUBTILE 3
-#endif
-#ifndef GH_ENC_POLL_SLEEP_NS
-#define GH_ENC_POLL_SLEEP_NS 0
-#endif
-constexpr unsigned kEncPollSleepNs = GH_ENC_POLL_SLEEP_NS;  // pause between two polls of an unpublished tile state
-constexpr int kEncLookDepth = GH_ENC_LOOK_DEPTH;        // look-back rounds whose loads are in flight together
-constexpr int kEncTicketSubTile = GH_ENC_TICKET_SUBTILE;  // sub-tile during which the block draws its next tile
+constexpr int kEncGroupThreads = 256;
+constexpr int kEncGroups = 4;
+constexpr int kEncThreads = kEncGroupThreads * kEncGroups;  // one CTA per SM
+constexpr int kEncGroupWarps = kEncGroupThreads / 32;
+constexpr int kEncBytesPerThread = 32;
+constexpr int kEncChunks = kEncBytesPerThread / 4;                        // 64-bit chunks of four codewords
+constexpr int kEncSubTileBytes = kEncGroupThreads * kEncBytesPerThread;  // 8 KiB
+constexpr int kEncRowBytes = 32 * kEncBytesPerThread;                    // a warp's slice of a sub-tile
+constexpr int kEncMaxSubTiles = 2;
+constexpr int kEncMinTileBytes = kEncSubTileBytes;
+constexpr int kEncLookDepth = 3;    // predecessors per lane and look-back round
+constexpr u32 kEncLongFlag = 0x1000u;  // in the low half of a table entry: codeword longer than 16 bits
 
-// Shared memory of the encode kernel, per variant (kSymsPerChunk = 4: no code longer than 16 bits; 2: up to 32).
-//  * The (codeword, length) table is REPLICATED across the banks so that the per-byte gather is (nearly) free of
-//    bank conflicts: with one copy, 32 lanes looking up 32 random bytes cost ~4 wavefronts per LDS and the L1 data
-//    pipe was as busy as the ALUs (profiles/r2b: 262 M shared-load wavefronts for 67 M lookups).
-//      variant 4: 64-bit entries  (code << 16 | len, 1 << len), 8 copies: slot (sym * 8 + lane % 8)     -- 16 KiB
-//                 (the power of two lets the packer concatenate with multiply-adds on the FMA pipe instead of
-//                 funnel shifts on the ALU pipe, which is the pipe this kernel saturates)
-//      variant 2: 64-bit entries (len << 32) | code,  4 copies: slot (sym * 4 + lane % 4)              --  8 KiB
-//    Lanes that share a copy are served by one broadcast when their bytes are equal, else serially.
-//  * staging: worst case per sub-tile = 4096 symbols x max code length (+ end mark, + slack for the funnel shift).
-//    Variant 4 rotates THREE staging buffers so that one barrier per sub-tile is enough (see the kernel).
-template <int kSymsPerChunk>
-struct EncSmem {
-  static constexpr int kMaxLen = kSymsPerChunk == 4 ? 16 : 32;
-  static constexpr int kStageWords = (kEncSubTileBytes * kMaxLen + 32 + 31) / 32 + 2;
-  static constexpr int kBuffers = kSymsPerChunk == 4 ? 3 : 2;
-  static constexpr int kCopies = kSymsPerChunk == 4 ? 8 : 4;
-  static constexpr int kEntryBytes = 8;
-  static constexpr int kSymStride = kCopies * kEntryBytes;  // bytes between consecutive symbols' entries
-  static constexpr int kLutWords = 256 * kSymStride / 4;
-  u32 lut[kLutWords];
-  u32 stage[kBuffers][kStageWords];
-  u32 warp_total[kEncSubTiles][kEncThreads / 32];
-  u32 carry[2];
-  u32 tile;
+// staging buffer of a group: worst case 16384 codewords of 16 bits, or 8192 of 32 bits, plus the end mark; four zero
+// words in front (staging ORs up to two words below a chunk's last word, copy-out reads word -1; 16-byte aligned
+// clearing) and slack behind
+constexpr int kEncStageFront = 4;
+constexpr int kEncStageWords = kEncMaxSubTiles * kEncSubTileBytes * 16 / 32 + 2 + 6;
+constexpr int kEncStageBytes = (kEncStageFront + kEncStageWords) * 4;
+
+// Shared memory. The replicated table must sit at the shared-window address 0x10000 so that a single PRMT can
+// assemble an entry's address from (0x01, byte value, lane * 8); the rest is laid out around it.
+constexpr u32 kEncLutAddr = 0x10000u;
+constexpr u32 kEncLutBytes = 256u * 256u;
+struct EncGroupCtl {
+  u32 wtot[2][kEncGroupWarps];  // warp totals of a sub-tile, double-buffered
   u64 tile_start;
+  u32 next_tile;
+  u32 pad[3];
+};
+struct EncLowSmem {  // at the start of dynamic shared memory
+  EncGroupCtl ctl[kEncGroups];
+  uint2 long_table[GH_NSYM + 1];  // (codeword, length) of every symbol, single copy: slow path and end mark
 };
 
 constexpr u64 kFlagMask = 3ull << 62;
@@ -100,581 +77,349 @@ constexpr u64 kFlagPrefix = 2ull << 62;     // value = global bit offset just af
 struct EncWorkspace {
   u64* tile_state;  // [ntiles]
   u32* head;        // [ntiles]
-  u32* ticket;      // tile dispenser (tiles are handed out in the order blocks ask for them)
+  u32* ticket;      // tile dispenser (tiles are handed out in the order groups ask for them)
 };
 
-__host__ __device__ inline u64 enc_num_tiles(u64 n) { return (n + kEncTileBytes - 1) / kEncTileBytes; }
+__host__ __device__ inline u64 enc_num_tiles(u64 n, u32 tile_bytes) { return (n + tile_bytes - 1) / tile_bytes; }
 
-// the one partial vector at the end of the input (kept out of line: it runs once per launch)
-__device__ __noinline__ uint4 load_ragged(const uint8_t* p, int cnt) {
-  u32 w[4] = {0, 0, 0, 0};
-  for (int k = 0; k < cnt; ++k) w[k >> 2] |= u32(p[k]) << (8 * (k & 3));
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// OR the low `len` bits of `acc` (len in 1..64, higher bits of acc zero) into the staging bit string at bit
-// position `pos`. Worked from the value's last bit: it is shifted left by the free bits r that remain after it in
-// its last word, which gives the (up to) three words directly -- three shifts, no 64-bit left-justification.
-__device__ __forceinline__ void stage_bits(u32* stage, u32 pos, u64 acc, u32 len) {
-#ifdef GH_PROBE_NO_STAGE  // tuning probe (wrong output): one plain store instead of up to three atomics
-  stage[pos >> 5] = u32(acc) + len;
-  return;
+// ---- named barrier of one group -----------------------------------------------------------------------------------
+__device__ __forceinline__ void group_barrier(unsigned group) {
+#ifdef GH_EMUL
+  gh_emul::named_barrier(group + 1, kEncGroupThreads);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kEncGroupThreads) : "memory");
 #endif
-  const u32 end = pos + len;           // one past the last bit
-  const u32 w_first = pos >> 5;
-  const u32 w_last = (end - 1) >> 5;
-  const u32 r = (0u - end) & 31u;      // free bits after the value inside word w_last
-  const u32 lo = u32(acc), hi = u32(acc >> 32);
-  atomicOr(stage + w_last, lo << r);
-  if (w_last > w_first) atomicOr(stage + w_last - 1, __funnelshift_l(lo, hi, r));
-  if (w_last > w_first + 1) atomicOr(stage + w_last - 2, __funnelshift_l(hi, 0u, r));  // hi >> (32 - r), 0 when r == 0
 }
 
-// byte k of a 16-byte vector, zero-extended: one PRMT (the scaling to a table offset is then an IMAD on the FMA pipe;
-// as shift + mask the extraction costs two instructions on the ALU pipe, which is the pipe this kernel saturates)
-__device__ __forceinline__ u32 vec_byte(const uint4& v, int k) {
-  const u32 w = (k >> 2) == 0 ? v.x : (k >> 2) == 1 ? v.y : (k >> 2) == 2 ? v.z : v.w;
-  return __byte_perm(w, 0u, 0x4440u | u32(k & 3));
+// ---- table gather --------------------------------------------------------------------------------------------------
+#ifdef GH_EMUL
+typedef const unsigned char* enc_lut_t;  // the table's base plus this lane's column
+__device__ __forceinline__ uint2 enc_lut_entry(enc_lut_t lut_lane, u32 word, int k) {
+  return *reinterpret_cast<const uint2*>(lut_lane + (((word >> (8 * k)) & 0xffu) << 8));
+}
+#else
+typedef u32 enc_lut_t;  // kEncLutAddr | lane * 8
+__device__ __forceinline__ uint2 enc_lut_entry(enc_lut_t lut_lane, u32 word, int k) {
+  // address = 0x00 0x01 <byte k of word> <lane * 8>: bytes 3 and 2 and 0 from lut_lane, byte 1 from the input word
+  const u32 addr = __byte_perm(word, lut_lane, 0x7604u | (u32(k) << 4));
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+#endif
+
+// ---- staging -------------------------------------------------------------------------------------------------------
+// The staging buffer is addressed by its shared-window address (device) so that the ORs are RED.OR [reg + imm] without
+// generic-pointer arithmetic.
+#ifdef GH_EMUL
+typedef u32* enc_stage_t;
+__device__ __forceinline__ enc_stage_t enc_stage_handle(u32* p) { return p; }
+__device__ __forceinline__ void enc_stage_or(enc_stage_t st, u32 word, int delta, u32 v) { atomicOr(st + int(word) + delta, v); }
+__device__ __forceinline__ void enc_stage_or_nz(enc_stage_t st, u32 word, int delta, u32 v) {
+  if (v) atomicOr(st + int(word) + delta, v);
+}
+__device__ __forceinline__ u32 enc_stage_ld(enc_stage_t st, u32 word, int delta) { return st[int(word) + delta]; }
+#else
+typedef u32 enc_stage_t;
+__device__ __forceinline__ enc_stage_t enc_stage_handle(u32* p) { return u32(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void enc_stage_or(enc_stage_t st, u32 word, int delta, u32 v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(st + word * 4u + u32(delta * 4)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void enc_stage_or_nz(enc_stage_t st, u32 word, int delta, u32 v) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p red.shared.or.b32 [%0], %1;\n}" ::"r"(st + word * 4u + u32(delta * 4)), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ u32 enc_stage_ld(enc_stage_t st, u32 word, int delta) {
+  u32 v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(st + word * 4u + u32(delta * 4)) : "memory");
+  return v;
+}
+#endif
+
+// OR the low `len` bits of hi:lo (len in 1..64, higher bits zero) into the bit string so that they end just before
+// bit `end` (= position + len). With W = end / 32 and e = end % 32, word W takes the value's last e bits at its top
+// ((lo:0) >> e), word W-1 the 32 bits before them ((hi:lo) >> e) and word W-2 the rest (hi >> e): three funnel shifts
+// by `end` itself (SHF takes its distance modulo 32), no other arithmetic. Words that receive nothing are OR-ed with
+// zero (W, W-1) or skipped (W-2, rarely non-zero): the buffer has spare words on both sides.
+__device__ __forceinline__ void stage_chunk(enc_stage_t stage, u32 end, u32 lo, u32 hi) {
+  const u32 w = end >> 5;
+  enc_stage_or(stage, w, 0, __funnelshift_r(0u, lo, end));
+  enc_stage_or(stage, w, -1, __funnelshift_r(lo, hi, end));
+  enc_stage_or_nz(stage, w, -2, __funnelshift_r(hi, 0u, end));
 }
 
-// Decoupled look-back (Merrill & Garland) by one whole warp: publishes this tile's bit count, adds up the
-// predecessors' counts back to the nearest tile that already knows its start, publishes this tile's end bit and
-// returns its start bit (all 32 lanes must call it together).
+struct EncVec {
+  u32 w[8];
+};
+
+__device__ __forceinline__ EncVec enc_load_vec(const uint8_t* p, bool aligned32) {
+  const Unit8 u = ldg_unit(p, aligned32);
+  EncVec v;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v.w[k] = u.w[k];
+  return v;
+}
+
+// slow path: bit count / staging of the `cnt` bytes at p, codeword by codeword (bytes re-read from global memory)
+__device__ __noinline__ u32 count_slow(const uint2* long_table, const uint8_t* p, int cnt) {
+  u32 bits = 0;
+  for (int k = 0; k < cnt; ++k) bits += long_table[p[k]].y;
+  return bits;
+}
+__device__ __noinline__ u32 stage_slow(enc_stage_t stage, u32 pos, const uint2* long_table, const uint8_t* p, int cnt) {
+  for (int k = 0; k < cnt; ++k) {
+    const uint2 e = long_table[p[k]];
+    pos += e.y;
+    if (e.y) stage_chunk(stage, pos, e.x, 0u);
+  }
+  return pos;
+}
+
+// Decoupled look-back by one whole warp. The tile's own count was published as an AGGREGATE before (tiles > 0);
+// this adds up the predecessors' counts back to the nearest tile that already knows its start, publishes this
+// tile's end bit and returns its start bit (all 32 lanes must call it together).
 __device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 tile, u32 tile_bits, u64 start_bit, unsigned lane) {
   u64 exclusive = start_bit;
   if (tile == 0) {
     if (lane == 0) st_volatile_u64(ws.tile_state, kFlagPrefix | (start_bit + tile_bits));
-  } else {
-    if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
-    exclusive = 0;
-    long long look = (long long)tile - 1;
-    bool done = false;
-#ifdef GH_PROBE_NO_LOOKBACK  // tuning probe (wrong output): pretend every tile is 6 bits per byte
-    exclusive = start_bit + tile * u64(kEncTileBytes) * 6;
-    done = true;
-#endif
-    while (!done) {
-      // One round trip covers 32 x kEncLookDepth predecessors: lane l owns the kEncLookDepth consecutive tiles
-      // look - l * kEncLookDepth - r (r = 0 nearest), loads all of them at once, folds them locally (sum of
-      // aggregates up to and including its nearest PREFIX) and the warp then needs ONE ballot + ONE sum.
-      // The kernel's throughput is capped at (tiles covered per round) / (round time): tiles that cannot find
-      // a prefix in a round queue up behind those that can, so the window per round is what has to be wide.
-      const long long first_idx = look - (long long)lane * kEncLookDepth;
-      u64 st[kEncLookDepth];
-#pragma unroll
-      for (int r = 0; r < kEncLookDepth; ++r) {
-        const long long idx = first_idx - r;
-        st[r] = idx >= 0 ? ld_volatile_u64(ws.tile_state + idx) : kFlagPrefix;  // virtual tiles before tile 0 add nothing
-      }
-      u64 local = 0;
-      bool local_prefix = false;
-#pragma unroll
-      for (int r = 0; r < kEncLookDepth; ++r) {
-        const long long idx = first_idx - r;
-        while ((st[r] & kFlagMask) == 0) {  // not published yet
-          if (kEncPollSleepNs) __nanosleep(kEncPollSleepNs);
-          st[r] = ld_volatile_u64(ws.tile_state + idx);
-        }
-        if (!local_prefix) local += st[r] & ~kFlagMask;
-        local_prefix = local_prefix || (st[r] & kFlagMask) == kFlagPrefix;
-      }
-      const unsigned has_prefix = __ballot_sync(0xffffffffu, local_prefix);
-      // lanes up to and including the nearest one that found a prefix contribute
-      const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
-      const u64 contrib = (has_prefix == 0 || lane <= first) ? local : 0ull;
-      exclusive += warp_sum64(contrib);
-      done = has_prefix != 0;
-      look -= 32 * kEncLookDepth;
-    }
-    if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
+    return exclusive;
   }
+  exclusive = 0;
+  long long look = (long long)tile - 1;
+  bool done = false;
+  while (!done) {
+    // One round trip covers 32 x kEncLookDepth predecessors: lane l owns the consecutive tiles
+    // look - l * kEncLookDepth - r (r = 0 nearest), loads all of them at once, folds them locally (sum of
+    // aggregates up to and including its nearest PREFIX) and the warp then needs ONE ballot + ONE sum.
+    const long long first_idx = look - (long long)lane * kEncLookDepth;
+    u64 st[kEncLookDepth];
+#pragma unroll
+    for (int r = 0; r < kEncLookDepth; ++r) {
+      const long long idx = first_idx - r;
+      st[r] = idx >= 0 ? ld_volatile_u64(ws.tile_state + idx) : kFlagPrefix;  // virtual tiles before tile 0 add nothing
+    }
+    u64 local = 0;
+    bool local_prefix = false;
+#pragma unroll
+    for (int r = 0; r < kEncLookDepth; ++r) {
+      const long long idx = first_idx - r;
+      while ((st[r] & kFlagMask) == 0) st[r] = ld_volatile_u64(ws.tile_state + idx);  // not published yet
+      if (!local_prefix) local += st[r] & ~kFlagMask;
+      local_prefix = local_prefix || (st[r] & kFlagMask) == kFlagPrefix;
+    }
+    const unsigned has_prefix = __ballot_sync(0xffffffffu, local_prefix);
+    // lanes up to and including the nearest one that found a prefix contribute
+    const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
+    const u64 contrib = (has_prefix == 0 || lane <= first) ? local : 0ull;
+    exclusive += warp_sum64(contrib);
+    done = has_prefix != 0;
+    look -= 32 * kEncLookDepth;
+  }
+  if (lane == 0) st_volatile_u64(ws.tile_state + tile, kFlagPrefix | (exclusive + tile_bits));
   return exclusive;
-
 }
 
-// gather from this lane's copy of the table (see EncSmem)
-template <int kSymsPerChunk>
-__device__ __forceinline__ u32 lut_word(smem_addr_t lut_lane, u32 byte) {  // variant 4: code << 16 | len; variant 2: len
-  typedef EncSmem<kSymsPerChunk> Smem;
-  return lds_u32(lut_lane, byte * u32(Smem::kSymStride) + (kSymsPerChunk == 4 ? 0u : 4u));
-}
-template <int kSymsPerChunk>
-__device__ __forceinline__ void lut_entry(smem_addr_t lut_lane, u32 byte, u32& code, u32& len) {
-  typedef EncSmem<kSymsPerChunk> Smem;
-  if (kSymsPerChunk == 4) {
-    const u32 e = lds_u32(lut_lane, byte * u32(Smem::kSymStride));
-    code = e >> 16;
-    len = e & 0xffffu;
-  } else {
-    const uint2 e = lds_v2(lut_lane, byte * u32(Smem::kSymStride));
-    code = e.x;
-    len = e.y;
-  }
-}
-
-// one 64-bit chunk of the short-code variant from four table entries (code << 16 | len, 1 << len): acc = acc * 2^len
-// + code on the FMA pipe (see the kernel); returns the chunk's bit length
-__device__ __forceinline__ u32 build_chunk4(const uint2& e0, const uint2& e1, const uint2& e2, const uint2& e3, u32& lo, u32& hi) {
-  const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
-  const u64 p2 = u64(a01) * e2.y;                                               // <= 48 bits
-  const u32 lo2 = u32(p2) + __umulhi(e2.x, 1u << 16), hi2 = u32(p2 >> 32);
-  const u64 p3 = u64(lo2) * e3.y;
-  lo = u32(p3) + __umulhi(e3.x, 1u << 16);
-  hi = hi2 * e3.y + u32(p3 >> 32);
-  return (e0.x + e1.x + e2.x + e3.x) & 0xffffu;
-}
-
-template <int kSymsPerChunk>
-__global__ void __launch_bounds__(kEncThreads, kEncBlocksPerSm)
+template <int kSubTiles>
+__global__ void __launch_bounds__(kEncThreads, 1)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
-              u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
-  constexpr int kChunks = kEncBytesPerThread / kSymsPerChunk;
-  typedef EncSmem<kSymsPerChunk> Smem;
+              u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws,
+              u32 smem_bytes) {
+  constexpr u32 kTileBytes = u32(kSubTiles) * kEncSubTileBytes;
   GH_DYNAMIC_SMEM(smem_raw);
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  u32(&s_stage)[Smem::kBuffers][Smem::kStageWords] = sm.stage;
-  u32(&s_warp_total)[kEncSubTiles][kEncThreads / 32] = sm.warp_total;
-  u32(&s_carry)[2] = sm.carry;
-  u32& s_tile = sm.tile;
-  u64& s_tile_start = sm.tile_start;
+  const unsigned group = threadIdx.x / kEncGroupThreads, tg = threadIdx.x % kEncGroupThreads;
+  const unsigned lane = tg & 31, wg = tg >> 5;
 
-  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (t == 0) s_tile = atomicAdd(ws.ticket, 1u);
-  for (unsigned i = t; i < 256u * Smem::kCopies; i += kEncThreads) {
-    const unsigned sym = i / Smem::kCopies;
-    if (kSymsPerChunk == 4) {
-      sm.lut[2 * i] = (table.codeword[sym] << 16) | table.length[sym];
-      sm.lut[2 * i + 1] = 1u << table.length[sym];
-    } else {
-      sm.lut[2 * i] = table.codeword[sym];
-      sm.lut[2 * i + 1] = table.length[sym];
-    }
-  }
-  for (unsigned i = t; i < unsigned(Smem::kBuffers) * Smem::kStageWords; i += kEncThreads) (&s_stage[0][0])[i] = 0;
-  __syncthreads();
-  // this lane's copy of the table: entry of byte b at lut_lane + b * kSymStride
-  const smem_addr_t lut_lane = smem_addr(sm.lut) + (lane & u32(Smem::kCopies - 1)) * u32(Smem::kEntryBytes);
-  u32 buf = 0;        // staging buffer of the current sub-tile (rotates through kBuffers)
-  u32 prev_words = 0; // variant 4: words of the previous sub-tile's buffer that still have to be cleared
-  const u64 ntiles = enc_num_tiles(n);
-  const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
-  const u32 eof_len_all = table.length[GH_EOF_SYMBOL];
-
-  for (u64 tile = s_tile; tile < ntiles; tile = s_tile) {
-    const bool last_tile = (tile + 1 == ntiles);
-    // ---- 1. all loads of the tile up front, bit count per sub-tile ---------------------------------------
-    uint4 raw[kEncSubTiles];
-    int cnt[kEncSubTiles];
-#pragma unroll
-    for (int j = 0; j < kEncSubTiles; ++j) {
-      const u64 base = tile * kEncTileBytes + u64(j) * kEncSubTileBytes + u64(t) * kEncBytesPerThread;
-      raw[j] = make_uint4(0, 0, 0, 0);
-      cnt[j] = 0;
-      if (base + kEncBytesPerThread <= n) {
-        raw[j] = ldg128(reinterpret_cast<const uint4*>(in + base));
-        cnt[j] = kEncBytesPerThread;
-      } else if (base < n) {
-        cnt[j] = int(n - base);
-        raw[j] = load_ragged(in + base, cnt[j]);
-      }
-    }
-    u32 bits[kEncSubTiles];
-    int end_sub = -1;  // the sub-tile in which this thread owns the last input byte (it carries the end mark)
-    constexpr bool kFused = GH_ENC_FUSED && kSymsPerChunk == 4;
-    u32 ch_lo[kFused ? kEncSubTiles : 1][4], ch_hi[kFused ? kEncSubTiles : 1][4], ch_len[kFused ? kEncSubTiles : 1];
-#pragma unroll
-    for (int j = 0; j < kEncSubTiles; ++j) {
-      u32 b = 0;
-      if (kFused) {
-        // missing symbols of the ragged last vector count as (code 0, length 0, 2^0)
-        const bool whole = cnt[j] == kEncBytesPerThread;  // all but the one ragged vector at the end of the input
-        auto entry = [&](int k) -> uint2 {
-          return (whole || k < cnt[j]) ? lds_v2(lut_lane, vec_byte(raw[j], k) * u32(Smem::kSymStride)) : make_uint2(0u, 1u);
-        };
-        u32 lens = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const u32 clen = build_chunk4(entry(4 * c), entry(4 * c + 1), entry(4 * c + 2), entry(4 * c + 3),
-                                        ch_lo[kFused ? j : 0][c], ch_hi[kFused ? j : 0][c]);
-          lens |= clen << (8 * c);  // <= 64 each
-          b += clen;
-        }
-        ch_len[kFused ? j : 0] = lens;
-      } else
-#ifdef GH_PROBE_NO_COUNT  // tuning probe (wrong output): no length gather
-      b = 6u * u32(cnt[j]) + (raw[j].x & 1u);
-      if (false)
+  // ---- carve shared memory around the table's fixed address ------------------------------------------------------
+  EncLowSmem& low = *reinterpret_cast<EncLowSmem*>(smem_raw);
+#ifdef GH_EMUL
+  const u32 lut_off = kEncLutAddr - 0x400u;
+#else
+  const u32 smem_base = u32(__cvta_generic_to_shared(smem_raw));
+  const u32 lut_off = kEncLutAddr - smem_base;
+  if (smem_base > kEncLutAddr - u32(sizeof(EncLowSmem)) - u32(kEncStageBytes) - 16u ||
+      lut_off + kEncLutBytes + 3u * u32(kEncStageBytes) > smem_bytes)
+    __trap();  // the launch did not provide the window this layout needs
 #endif
-      // variant 4 sums whole entries: the lengths (<= 16 x 16) add up in the low half, the codes above them
-      if (cnt[j] == kEncBytesPerThread) {
-#pragma unroll
-        for (int k = 0; k < kEncBytesPerThread; ++k) b += lut_word<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
-      } else {
-        for (int k = 0; k < cnt[j]; ++k) b += lut_word<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k));
-      }
-      if (kSymsPerChunk == 4) b &= 0xffffu;
-      const u64 base = tile * kEncTileBytes + u64(j) * kEncSubTileBytes + u64(t) * kEncBytesPerThread;
-      if (append_eof && last_tile && base < n && base + kEncBytesPerThread >= n) {
-        end_sub = j;
-        b += eof_len_all;
-      }
-      bits[j] = b;
-    }
+  (void)smem_bytes;
+  unsigned char* const lut_ptr = smem_raw + lut_off;
+  // group 0 stages below the table, groups 1..3 above it
+  u32* const stage_base = group == 0
+                              ? reinterpret_cast<u32*>(smem_raw + ((sizeof(EncLowSmem) + 15) & ~size_t(15)))
+                              : reinterpret_cast<u32*>(lut_ptr + kEncLutBytes + size_t(group - 1) * kEncStageBytes);
+  u32* const stage_ptr = stage_base + kEncStageFront;
+  const enc_stage_t stage = enc_stage_handle(stage_ptr);
+  EncGroupCtl& ctl = low.ctl[group];
 
-    // ---- 2. per-sub-tile block scans; warp 0 resolves the global offset while the others start packing ----
-    u32 incl[kEncSubTiles];
+  // ---- tables (once per CTA) ---------------------------------------------------------------------------------------
+  for (unsigned i = threadIdx.x; i < 256u * 32u; i += kEncThreads) {
+    const unsigned sym = i >> 5, col = i & 31;
+    const u32 len = table.length[sym];
+    uint2 e;
+    if (len == 0) e = make_uint2(0u, 1u);                                     // byte value that does not occur
+    else if (len <= 16) e = make_uint2((table.codeword[sym] << 16) | len, 1u << len);
+    else e = make_uint2(kEncLongFlag, 1u);                                    // handled by the slow path
+    *reinterpret_cast<uint2*>(lut_ptr + sym * 256u + col * 8u) = e;
+  }
+  for (unsigned i = threadIdx.x; i < unsigned(GH_NSYM); i += kEncThreads)
+    low.long_table[i] = make_uint2(table.codeword[i], u32(table.length[i]));
+  for (unsigned i = tg; i < unsigned(kEncStageFront + kEncStageWords); i += kEncGroupThreads) stage_base[i] = 0;
+  if (tg == 0) ctl.next_tile = atomicAdd(ws.ticket, 1u);
+  __syncthreads();
+#ifdef GH_EMUL
+  const enc_lut_t lut_lane = lut_ptr + lane * 8u;
+#else
+  const enc_lut_t lut_lane = kEncLutAddr | (lane * 8u);
+#endif
+  const uint2* const long_table = low.long_table;
+  const u64 ntiles = enc_num_tiles(n, kTileBytes);
+  const bool aligned32 = (reinterpret_cast<uintptr_t>(in) & 31) == 0;
+  const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
+  const u32 eof_len = append_eof ? u32(table.length[GH_EOF_SYMBOL]) : 0u;
+  const u32 toff = tg * kEncBytesPerThread;           // this thread's slice inside a sub-tile
+  const u32 roff = (tg & ~31u) * kEncBytesPerThread;  // its warp's row
+  u32 wpar = 0;  // slot of wtot the next sub-tile uses
+
+  u64 tile = ctl.next_tile;
+  while (tile < ntiles) {
+    const u64 tile_base = tile * kTileBytes;
+    const uint8_t* const tin = in + tile_base;
+    const u64 left = n - tile_base;
+    const u32 rem = left < u64(kTileBytes) ? u32(left) : kTileBytes;  // bytes of this tile (short only for the last one)
+    const bool last_tile = (tile + 1 == ntiles);
+    // all of the tile's loads up front
+    EncVec vec[kSubTiles];
 #pragma unroll
-    for (int j = 0; j < kEncSubTiles; ++j) {
-      incl[j] = warp_inclusive_scan(bits[j], lane);
-      if (lane == 31) s_warp_total[j][warp] = incl[j];
+    for (int j = 0; j < kSubTiles; ++j) {
+      const u32 off = u32(j) * kEncSubTileBytes + toff;
+      if (off + kEncBytesPerThread <= rem) {
+        vec[j] = enc_load_vec(tin + off, aligned32);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) vec[j].w[k] = 0;
+      }
     }
-    __syncthreads();  // (a)
-    u32 sub_bits[kEncSubTiles];  // bits of each sub-tile
-    u32 pos0[kEncSubTiles];      // sub-tile-relative bit position of this thread's first bit
+    u32 sub_base = 0;  // bits of this tile in earlier sub-tiles
     u32 tile_bits = 0;
 #pragma unroll
-    for (int j = 0; j < kEncSubTiles; ++j) {
-      u32 wb = 0, tot = 0;
+    for (int j = 0; j < kSubTiles; ++j) {
+      const u32 off = u32(j) * kEncSubTileBytes + toff;
+      const u32 row = u32(j) * kEncSubTileBytes + roff;
+      // ---- 1. gather + concatenate ---------------------------------------------------------------------------
+      u32 c_lo[kEncChunks], c_hi[kEncChunks], c_end[kEncChunks];
+      u32 bits = 0, flags = 0;
 #pragma unroll
-      for (int k = 0; k < kEncThreads / 32; ++k) {
-        const u32 wt = s_warp_total[j][k];
-        if (unsigned(k) < warp) wb += wt;
-        tot += wt;
+      for (int c = 0; c < kEncChunks; ++c) {
+        const u32 word = vec[j].w[c];
+        const uint2 e0 = enc_lut_entry(lut_lane, word, 0);
+        const uint2 e1 = enc_lut_entry(lut_lane, word, 1);
+        const uint2 e2 = enc_lut_entry(lut_lane, word, 2);
+        const uint2 e3 = enc_lut_entry(lut_lane, word, 3);
+        // acc = ((c0 * 2^l1 + c1) * 2^l2 * 2^l3) + (c2 * 2^l3 + c3): products on the FMA pipe; the additions cannot
+        // carry because the products' low bits are zero
+        const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
+        const u32 a23 = __umulhi(e2.x, 1u << 16) * e3.y + __umulhi(e3.x, 1u << 16);  // <= 32 bits
+        const u64 t = u64(a01) * e2.y;                                               // <= 48 bits
+        const u64 acc = t * e3.y + a23;
+        c_lo[c] = u32(acc);
+        c_hi[c] = u32(acc >> 32);
+        const u32 l = (e0.x + e1.x + e2.x + e3.x) & 0xffffu;  // lengths (and long-codeword flags) add up in the low half
+        flags |= l;
+        bits += l;
+        c_end[c] = bits;  // end of this chunk relative to the thread's first bit
       }
-      sub_bits[j] = tot;
-      pos0[j] = wb + incl[j] - bits[j];
-      tile_bits += tot;
-    }
-
-    if (warp == 0) {
-      const u64 exclusive = tile_start_lookback(ws, tile, tile_bits, start_bit, lane);
-      if (lane == 0) s_tile_start = exclusive;
-    }
-
-    // ---- 3 + 4. sub-tile by sub-tile: pack (tile-relative), then copy out with the phase shift ------------
-    u32 before = 0;  // bits of this tile in earlier sub-tiles
-#pragma unroll
-    for (int j = 0; j < kEncSubTiles; ++j) {
-      u32* stage = s_stage[buf];
-      {
-        u32 pos = pos0[j];
-        if (kFused) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const u32 clen = (ch_len[kFused ? j : 0] >> (8 * c)) & 0xffu;
-            if (clen) stage_bits(stage, pos, (u64(ch_hi[kFused ? j : 0][c]) << 32) | ch_lo[kFused ? j : 0][c], clen);
-            pos += clen;
-          }
-        } else
-#ifdef GH_PROBE_NO_PACK  // tuning probe (wrong output): no code gather, no concatenation, no staging
-        if (false)
-#endif
-        if (cnt[j] == kEncBytesPerThread) {
-#pragma unroll
-          for (int c = 0; c < kChunks; ++c) {
-            u64 acc = 0;
-            u32 clen = 0;
-            if (kSymsPerChunk == 4) {
-              // entries are (code << 16 | len, 1 << len) with len <= 16. acc = acc * 2^len + code, all on the FMA
-              // pipe: the code is the high half of the entry (IMAD.HI), the products are IMAD / IMAD.WIDE, and adding
-              // the code cannot carry because the product's low len bits are zero. Lengths are summed as whole
-              // entries (they are the low halves and cannot carry into the codes) and masked once.
-              const uint2 e0 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 0) * u32(Smem::kSymStride));
-              const uint2 e1 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 1) * u32(Smem::kSymStride));
-              const uint2 e2 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 2) * u32(Smem::kSymStride));
-              const uint2 e3 = lds_v2(lut_lane, vec_byte(raw[j], c * 4 + 3) * u32(Smem::kSymStride));
-              const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
-              const u64 p2 = u64(a01) * e2.y;                                               // <= 48 bits
-              const u32 lo2 = u32(p2) + __umulhi(e2.x, 1u << 16), hi2 = u32(p2 >> 32);
-              const u64 p3 = u64(lo2) * e3.y;
-              const u32 lo3 = u32(p3) + __umulhi(e3.x, 1u << 16);
-              const u32 hi3 = hi2 * e3.y + u32(p3 >> 32);
-              acc = (u64(hi3) << 32) | lo3;
-              clen = (e0.x + e1.x + e2.x + e3.x) & 0xffffu;
-            } else {
-#pragma unroll
-              for (int q = 0; q < kSymsPerChunk; ++q) {
-                u32 code, len;
-                lut_entry<kSymsPerChunk>(lut_lane, vec_byte(raw[j], c * kSymsPerChunk + q), code, len);
-                acc = (acc << len) | code;  // len <= 32: at most 64 bits per chunk
-                clen += len;
-              }
-            }
-            stage_bits(stage, pos, acc, clen);  // every byte value that occurs has a code: clen >= kSymsPerChunk
-            pos += clen;
-          }
-        } else {  // the ragged last vector of the input: symbol by symbol
-          for (int k = 0; k < cnt[j]; ++k) {
-            u32 code, len;
-            lut_entry<kSymsPerChunk>(lut_lane, vec_byte(raw[j], k), code, len);
-            stage_bits(stage, pos, code, len);
-            pos += len;
-          }
+      // slices that need the slow path: a long codeword, the ragged end, or the byte the end mark follows
+      const bool row_live = row < rem;
+      const bool row_end = last_tile && row + kEncRowBytes >= rem;
+      bool slow = false;
+      int cnt = 0;
+      bool owns_end = false;
+      if (row_live) {
+        slow = row_end || __any_sync(0xffffffffu, (flags & 0xf000u) != 0u);
+        if (slow) {
+          cnt = off >= rem ? 0 : (rem - off < u32(kEncBytesPerThread) ? int(rem - off) : kEncBytesPerThread);
+          bits = count_slow(long_table, tin + off, cnt);
+          owns_end = last_tile && cnt > 0 && off + u32(cnt) == rem;
+          if (owns_end) bits += eof_len;
         }
-        if (end_sub == j && eof_len_all) stage_bits(stage, pos, eof_code, eof_len_all);
-      }
-      __syncthreads();  // (c_j) staging of sub-tile j complete; for j == 0 also: s_tile_start written
-      if (j == kEncTicketSubTile && t == 0) s_tile = atomicAdd(ws.ticket, 1u);  // next tile (read after a later barrier)
-
-      const u64 G = s_tile_start + before;  // global bit offset of this sub-tile
-      const u32 nbits = sub_bits[j];
-      const u32 phase = u32(G & 31);
-      const u64 end_bit = G + nbits;
-      const bool stream_end = last_tile && (before + nbits == tile_bits);  // no bits follow in the whole stream
-      const bool more_in_tile = before + nbits < tile_bits;                // a later sub-tile continues this word
-      u32 pad = 0;
-      if (append_eof && stream_end && nbits) pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s to the byte
-      if (stream_end && nbits && t == 0 && end_bit_out) *end_bit_out = end_bit;
-      const u64 word0 = G >> 5;
-      const u32 nwords = nbits ? u32((u64(phase) + nbits + pad + 31) >> 5) : 0u;
-      const bool partial_end = ((phase + nbits + pad) & 31) != 0;
-      const bool shared_head = (j == 0) && (tile > 0) && (phase != 0);
-#ifdef GH_PROBE_NO_COPYLOOP  // tuning probe (wrong output): no copy-out at all
-      if (false)
-#endif
-      {
-        // interior words (neither the first nor the last of the sub-tile) need none of the special cases: a lean
-        // loop (two LDS, one funnel shift, one byte swap, one store). Measured with the probe builds: the copy-out
-        // loop with all its cases inline cost 0.30 ms of the kernel's 1.73, its global stores almost nothing.
-        const bool fits = GH_ENC_LEAN_COPY(kSymsPerChunk) && word0 + nwords <= out_word_cap;
-        if (fits && nwords > 2u) {
-          u32* const dst = out_words + word0;
-          for (u32 i = t + 1u; i < nwords - 1u; i += kEncThreads) dst[i] = be32(__funnelshift_r(stage[i], stage[i - 1], phase));
-        }
-        // first and last word, and everything when the output might not fit
-        for (u32 i = t; i < nwords; i += kEncThreads) {
-          if (fits && i != 0u && i != nwords - 1u) continue;
-          u32 v = __funnelshift_r(stage[i], i ? stage[i - 1] : 0u, phase);
-          const u64 gw = word0 + i;
-          if (pad && gw == (end_bit >> 5)) v |= ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad));
-          if (i == 0 && j > 0 && phase != 0) v |= s_carry[(j - 1) & 1];  // tail of the previous sub-tile
-          if (i == nwords - 1 && partial_end && more_in_tile) s_carry[j & 1] = v;  // continued by the next sub-tile
-          else if (i == 0 && shared_head) ws.head[tile] = v;
-#ifdef GH_PROBE_NO_COPYOUT  // tuning probe (wrong output): only one word in 64 is stored
-          else if (gw < out_word_cap && (i & 63u) == 0u) out_words[gw] = be32(v);
-#else
-          else if (gw < out_word_cap) out_words[gw] = be32(v);
-#endif
-        }
-      }
-      if (Smem::kBuffers == 3) {
-        // One barrier per sub-tile: the buffer of the PREVIOUS sub-tile is cleared now -- a thread passes barrier
-        // (c_j) only after it has finished reading that buffer -- and it is packed into again after barrier
-        // (c_j+1), which no thread passes before every thread has finished this clearing.
-        u32* prev = s_stage[buf == 0 ? 2 : buf - 1];
-        for (u32 i = t; i < prev_words; i += kEncThreads) prev[i] = 0;
-        prev_words = (nbits >> 5) + 3;
-        buf = buf == 2 ? 0 : buf + 1;
       } else {
-        __syncthreads();  // (d_j) staged words consumed
-        for (u32 i = t; i < (nbits >> 5) + 3; i += kEncThreads) stage[i] = 0;  // clean for sub-tile j + 2
-        buf ^= 1;
+        bits = 0;
       }
-      before += nbits;
-    }
-    // the next tile's number was written after barrier (c_3) when it is drawn during the last sub-tile: one more
-    // barrier before it is read (the two-buffer variant has (d_3) for that)
-    if (Smem::kBuffers == 3 && kEncTicketSubTile == kEncSubTiles - 1) __syncthreads();
-  }
-}
-
-// ---- experimental: encoder with warp-independent phases (short codes only, GH_ENCODE_KERNEL=warp) -----------------
-// The probe builds (tools/enc_probe.py) show that the phases of encode_kernel add up: its barrier-separated phases
-// overlap too little. Here every warp owns a 2 KiB slice of the tile (kEncSubTiles rows of 32 lanes x 16 bytes) and a
-// staging area of its own, so that between the block-wide barriers the warps run their phases independently:
-//   count + warp scans -> barrier 1 (the eight warp totals) -> warp 0 looks back while every warp packs all its rows
-//   at warp-relative positions -> barrier 2 (the tile's start bit) -> every warp copies its own range out with its own
-//   phase; the first / last word of a warp's range, when shared with a neighbour, goes to a small edge array ->
-//   barrier 3 -> one thread merges the edges (and hands the tile's shared first word to head[], as encode_kernel does).
-// Same output, same workspace protocol (tile_state, head[], encode_stitch_kernel). Measured once (r3i, tools/
-// enc_warp_check.py): bit-identical to encode_kernel on the B200 and 1.71 ms vs 1.67 ms for 1 GiB Zipf at 4 blocks per
-// SM -- no gain as it stands, so it is not the default; kept as the starting point for the next round's experiments.
-#ifndef GH_ENC_WARP_BLOCKS
-#define GH_ENC_WARP_BLOCKS 4
-#endif
-struct EncWarpSmem {
-  static constexpr int kWarps = kEncThreads / 32;
-  static constexpr int kRows = kEncSubTiles;
-  static constexpr int kWarpBytes = kRows * 32 * kEncBytesPerThread;  // 2 KiB
-  static constexpr int kStageWords = (kWarpBytes * 16 + 32 + 31) / 32 + 2;
-  static constexpr int kCopies = 8;
-  static constexpr int kSymStride = kCopies * 8;
-  u32 lut[256 * kCopies * 2];
-  u32 stage[kWarps][kStageWords];
-  u32 wtot[kWarps];
-  u64 edge_word[kWarps][2];
-  u32 edge_val[kWarps][2];
-  u32 edge_n[kWarps];
-  u32 tile;
-  u64 tile_start;
-};
-static_assert(EncWarpSmem::kWarps * EncWarpSmem::kWarpBytes == kEncTileBytes, "a tile is one slice per warp");
-
-__global__ void __launch_bounds__(kEncThreads, GH_ENC_WARP_BLOCKS)
-encode_warp_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
-                   u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws) {
-  typedef EncWarpSmem Smem;
-  GH_DYNAMIC_SMEM(smem_raw);
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (t == 0) sm.tile = atomicAdd(ws.ticket, 1u);
-  for (unsigned i = t; i < 256u * Smem::kCopies; i += kEncThreads) {
-    const unsigned sym = i / Smem::kCopies;
-    sm.lut[2 * i] = (table.codeword[sym] << 16) | table.length[sym];
-    sm.lut[2 * i + 1] = 1u << table.length[sym];
-  }
-  for (unsigned i = t; i < unsigned(Smem::kWarps) * Smem::kStageWords; i += kEncThreads) (&sm.stage[0][0])[i] = 0;
-  __syncthreads();
-  const smem_addr_t lut_lane = smem_addr(sm.lut) + (lane & u32(Smem::kCopies - 1)) * 8u;
-  u32* const stage = sm.stage[warp];
-  const u64 ntiles = enc_num_tiles(n);
-  const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
-  const u32 eof_len = table.length[GH_EOF_SYMBOL];
-
-  for (u64 tile = sm.tile; tile < ntiles; tile = sm.tile) {
-    const bool last_tile = (tile + 1 == ntiles);
-    // ---- 1. loads and bit counts of this lane's kRows vectors -----------------------------------------------
-    uint4 raw[Smem::kRows];
-    int cnt[Smem::kRows];
-    u32 bits[Smem::kRows];
-    int end_row = -1;  // the row in which this lane owns the last input byte (it carries the end mark)
+      // ---- 2. scan ---------------------------------------------------------------------------------------------
+      const u32 incl = warp_inclusive_scan(bits, lane);
+      if (lane == 31) ctl.wtot[wpar][wg] = incl;
+      group_barrier(group);
+      u32 wprefix, sub_bits;
+      {
+        // the eight warp totals, scanned by every warp for itself
+        u32 v = lane < u32(kEncGroupWarps) ? ctl.wtot[wpar][lane] : 0u;
 #pragma unroll
-    for (int r = 0; r < Smem::kRows; ++r) {
-      const u64 base = tile * kEncTileBytes + u64(warp) * Smem::kWarpBytes + u64(r) * (32 * kEncBytesPerThread) +
-                       u64(lane) * kEncBytesPerThread;
-      raw[r] = make_uint4(0, 0, 0, 0);
-      cnt[r] = 0;
-      if (base + kEncBytesPerThread <= n) {
-        raw[r] = ldg128(reinterpret_cast<const uint4*>(in + base));
-        cnt[r] = kEncBytesPerThread;
-      } else if (base < n) {
-        cnt[r] = int(n - base);
-        raw[r] = load_ragged(in + base, cnt[r]);
+        for (int d = 1; d < kEncGroupWarps; d <<= 1) {
+          const u32 up = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= unsigned(d)) v += up;
+        }
+        sub_bits = __shfl_sync(0xffffffffu, v, kEncGroupWarps - 1);
+        const u32 mine = __shfl_sync(0xffffffffu, v, int(wg));
+        wprefix = mine - __shfl_sync(0xffffffffu, incl, 31);
       }
-    }
+      wpar ^= 1;
+      if (j == kSubTiles - 1) {
+        tile_bits = sub_base + sub_bits;
+        if (tg == 0 && tile > 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
+      }
+      // ---- 3. staging at tile-relative positions ----------------------------------------------------------------
+      const u32 pos = sub_base + wprefix + incl - bits;
+      if (!slow) {
+        if (row_live) {
 #pragma unroll
-    for (int r = 0; r < Smem::kRows; ++r) {
-      u32 b = 0;
-      if (cnt[r] == kEncBytesPerThread) {
-#pragma unroll
-        for (int k = 0; k < kEncBytesPerThread; ++k) b += lds_u32(lut_lane, vec_byte(raw[r], k) * u32(Smem::kSymStride));
+          for (int c = 0; c < kEncChunks; ++c) stage_chunk(stage, pos + c_end[c], c_lo[c], c_hi[c]);
+        }
       } else {
-        for (int k = 0; k < cnt[r]; ++k) b += lds_u32(lut_lane, vec_byte(raw[r], k) * u32(Smem::kSymStride));
+        const u32 p2 = stage_slow(stage, pos, long_table, tin + off, cnt);
+        if (owns_end && eof_len) stage_chunk(stage, p2 + eof_len, eof_code, 0u);
       }
-      b &= 0xffffu;  // whole entries were summed: the lengths are their low halves
-      const u64 base = tile * kEncTileBytes + u64(warp) * Smem::kWarpBytes + u64(r) * (32 * kEncBytesPerThread) +
-                       u64(lane) * kEncBytesPerThread;
-      if (append_eof && last_tile && base < n && base + kEncBytesPerThread >= n) {
-        end_row = r;
-        b += eof_len;
-      }
-      bits[r] = b;
+      sub_base += sub_bits;
     }
-    // ---- 2. warp-relative positions; the warp totals are all the block has to exchange -----------------------
-    u32 pos[Smem::kRows];
-    u32 wbits = 0;
-#pragma unroll
-    for (int r = 0; r < Smem::kRows; ++r) {
-      const u32 incl = warp_inclusive_scan(bits[r], lane);
-      pos[r] = wbits + incl - bits[r];
-      wbits += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) sm.wtot[warp] = wbits;
-    __syncthreads();  // (1)
-    u32 woff = 0, tile_bits = 0;
-#pragma unroll
-    for (int k = 0; k < Smem::kWarps; ++k) {
-      const u32 v = sm.wtot[k];
-      if (unsigned(k) < warp) woff += v;
-      tile_bits += v;
-    }
-    if (warp == 0) {
+
+    // ---- 4. the tile's start bit ---------------------------------------------------------------------------------
+    if (wg == 0) {
       const u64 exclusive = tile_start_lookback(ws, tile, tile_bits, start_bit, lane);
-      if (lane == 0) sm.tile_start = exclusive;
+      if (lane == 0) ctl.tile_start = exclusive;
     }
-    // ---- 3. pack all rows into the warp's own staging area ---------------------------------------------------
-#pragma unroll
-    for (int r = 0; r < Smem::kRows; ++r) {
-      u32 p = pos[r];
-      if (cnt[r] == kEncBytesPerThread) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          u32 lo, hi;
-          const u32 clen = build_chunk4(lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 0) * u32(Smem::kSymStride)),
-                                        lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 1) * u32(Smem::kSymStride)),
-                                        lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 2) * u32(Smem::kSymStride)),
-                                        lds_v2(lut_lane, vec_byte(raw[r], 4 * c + 3) * u32(Smem::kSymStride)), lo, hi);
-          stage_bits(stage, p, (u64(hi) << 32) | lo, clen);
-          p += clen;
-        }
-      } else {  // the ragged last vector of the input: symbol by symbol
-        for (int k = 0; k < cnt[r]; ++k) {
-          const u32 e = lds_u32(lut_lane, vec_byte(raw[r], k) * u32(Smem::kSymStride));
-          stage_bits(stage, p, e >> 16, e & 0xffffu);
-          p += e & 0xffffu;
-        }
-      }
-      if (end_row == r && eof_len) stage_bits(stage, p, eof_code, eof_len);
-    }
-    __syncthreads();  // (2) staging complete, tile start known
-    if (t == 0) sm.tile = atomicAdd(ws.ticket, 1u);  // next tile (read after barrier 3)
-    // ---- 4. copy-out of this warp's range --------------------------------------------------------------------
-    const u64 tile_G = sm.tile_start;
-    const u64 G = tile_G + woff;
-    const u32 nbits = wbits;
-    const u32 phase = u32(G & 31);
-    const u64 end_bit = G + nbits;
-    const bool stream_end = last_tile && nbits && (woff + nbits == tile_bits);  // no bits follow in the whole stream
-    u32 pad = 0;
-    if (append_eof && stream_end) pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s to the byte
-    if (stream_end && lane == 0 && end_bit_out) *end_bit_out = end_bit;
-    const u32 padmask = pad ? ((1u << pad) - 1u) << (32 - (u32(end_bit & 31) + pad)) : 0u;
+    group_barrier(group);  // staging complete, tile start known
+    // The next tile is drawn only now: a tile number that is held while its holder still waits for its own
+    // predecessors delays every later tile (they need this one's bit count), so it is held as briefly as possible.
+    if (tg == 0) ctl.next_tile = atomicAdd(ws.ticket, 1u);
+
+    // ---- 5. copy-out ------------------------------------------------------------------------------------------------
+    const u64 G = ctl.tile_start;
+    const u32 phase = u32(G) & 31u;
+    const u64 end_bit = G + tile_bits;
     const u64 word0 = G >> 5;
-    const u32 nwords = nbits ? u32((u64(phase) + nbits + pad + 31) >> 5) : 0u;
-    const bool head_partial = nwords && phase != 0;
-    const bool tail_partial = nwords && ((phase + nbits + pad) & 31) != 0 && !(nwords == 1 && head_partial);
-    const u32 lo_i = head_partial ? 1u : 0u, hi_i = nwords - (tail_partial ? 1u : 0u);
-    auto word_at = [&](u32 i) -> u32 {
-      u32 v = __funnelshift_r(stage[i], i ? stage[i - 1] : 0u, phase);
-      if (i == nwords - 1) v |= padmask;
-      return v;
-    };
-    for (u32 i = lo_i + lane; i < hi_i; i += 32) {
-      if (word0 + i < out_word_cap) out_words[word0 + i] = be32(word_at(i));
-    }
-    if (lane == 0) {  // words this warp shares with its neighbours
-      u32 ne = 0;
-      if (head_partial) sm.edge_word[warp][ne] = word0, sm.edge_val[warp][ne] = word_at(0), ++ne;
-      if (tail_partial) sm.edge_word[warp][ne] = word0 + nwords - 1, sm.edge_val[warp][ne] = word_at(nwords - 1), ++ne;
-      sm.edge_n[warp] = ne;
-    }
-    __syncwarp();
-    for (u32 i = lane; i < (nbits >> 5) + 3; i += 32) stage[i] = 0;  // clean for the next tile
-    __syncthreads();  // (3) edges written
-    if (t == 0) {
-      // contributions in stream order; equal word indices are merged; the tile's first word, when shared with the
-      // previous tile, goes to head[] (encode_stitch_kernel ORs it into what that tile stored)
-      const bool shared_head = tile > 0 && (tile_G & 31) != 0;
-      const u64 tile_word0 = tile_G >> 5;
-      u64 cur_word = ~0ull;
-      u32 cur_val = 0;
-      for (int w = 0; w <= Smem::kWarps; ++w) {
-        const u32 ne = w < Smem::kWarps ? sm.edge_n[w] : 1u;
-        for (u32 k = 0; k < ne; ++k) {
-          const u64 wd = w < Smem::kWarps ? sm.edge_word[w][k] : ~0ull;  // the extra round flushes the last word
-          const u32 v = w < Smem::kWarps ? sm.edge_val[w][k] : 0u;
-          if (wd != cur_word) {
-            if (cur_word != ~0ull) {
-              if (shared_head && cur_word == tile_word0) ws.head[tile] = cur_val;
-              else if (cur_word < out_word_cap) out_words[cur_word] = be32(cur_val);
-            }
-            cur_word = wd;
-            cur_val = v;
-          } else {
-            cur_val |= v;
-          }
+    const u32 nwords = (phase + tile_bits + 31u) >> 5;  // tile_bits > 0: every tile holds at least one codeword
+    if (last_tile && tg == 0 && end_bit_out) *end_bit_out = end_bit;
+    {
+      u32* const dst = out_words + word0;
+      const u64 room = out_word_cap > word0 ? out_word_cap - word0 : 0;
+      const u32 lim = u64(nwords - 1u) < room ? nwords - 1u : u32(room);  // interior words: 1 .. nwords - 2
+      for (u32 i = tg + 1u; i < lim; i += kEncGroupThreads)
+        dst[i] = be32(__funnelshift_r(enc_stage_ld(stage, i, 0), enc_stage_ld(stage, i, -1), phase));
+      // first and last word of the tile
+      if (tg < 2u && (tg == 0 || nwords > 1u)) {
+        const u32 i = tg == 0 ? 0u : nwords - 1u;
+        u32 v = __funnelshift_r(enc_stage_ld(stage, i, 0), enc_stage_ld(stage, i, -1), phase);
+        if (append_eof && last_tile && i == nwords - 1u) {
+          const u32 pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s up to the byte boundary
+          if (pad) v |= ((1u << pad) - 1u) << (32u - (u32(end_bit & 31) + pad));
         }
+        if (i == 0 && tile > 0 && phase != 0) ws.head[tile] = v;  // shared with the previous tile: stitched later
+        else if (u64(i) < room) dst[i] = be32(v);
       }
+    }
+    group_barrier(group);  // every staged word has been read, the next tile's number is there
+    tile = ctl.next_tile;
+    {
+      uint4* const z = reinterpret_cast<uint4*>(stage_ptr);
+      for (u32 i = tg; i < (tile_bits >> 7) + 1u; i += kEncGroupThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
@@ -682,7 +427,7 @@ encode_warp_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable tabl
 // Second kernel: OR each tile's deferred head bits into the word its predecessor stored.
 // Thread = tile. The first tile (in order) holding head bits for a given word merges the whole run.
 __global__ void __launch_bounds__(256)
-encode_stitch_kernel(u64 ntiles, u64 start_bit, u32* __restrict__ out_words, u64 out_word_cap, EncWorkspace ws) {
+encode_stitch_kernel(u64 ntiles, u32* __restrict__ out_words, u64 out_word_cap, EncWorkspace ws) {
   const u64 tile = u64(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tile == 0 || tile >= ntiles) return;
   const u64 g = ws.tile_state[tile - 1] & ~kFlagMask;  // global start bit of `tile`
@@ -692,7 +437,6 @@ encode_stitch_kernel(u64 ntiles, u64 start_bit, u32* __restrict__ out_words, u64
     const u64 gp = ws.tile_state[tile - 2] & ~kFlagMask;  // start of the previous tile
     if ((gp >> 5) == word && (gp & 31) != 0) return;       // the previous tile deferred into this word too: it leads
   }
-  (void)start_bit;
   u32 bits = ws.head[tile];
   for (u64 nx = tile + 1; nx < ntiles; ++nx) {  // only ever iterates for degenerate sub-word tiles
     const u64 gn = ws.tile_state[nx - 1] & ~kFlagMask;
@@ -703,7 +447,7 @@ encode_stitch_kernel(u64 ntiles, u64 start_bit, u32* __restrict__ out_words, u64
 }
 
 inline size_t enc_ws_bytes(u64 n) {
-  const u64 nt = enc_num_tiles(n) + 1;
+  const u64 nt = enc_num_tiles(n, kEncMinTileBytes) + 1;
   return size_t(nt * 8 + ((nt * 4 + 7) / 8) * 8 + 256);
 }
 
@@ -744,8 +488,13 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   EncodeTable table;
   int rc = build_encode_table(code, &table);
   if (rc != GH_OK) return rc;
-  const u64 ntiles = enc_num_tiles(n);
-  if (ntiles > 0x7fffffffull) return GH_ERR_ARG;
+  // codewords of byte values longer than 16 bits take the slow path and halve the tile (the end mark's own length
+  // does not matter: it is staged once, by the slow path)
+  bool long_codes = false;
+  for (int s = 0; s < 256; ++s) long_codes = long_codes || table.length[s] > 16;
+  const u32 tile_bytes = long_codes ? kEncSubTileBytes : 2 * kEncSubTileBytes;
+  const u64 ntiles = enc_num_tiles(n, tile_bytes);
+  if (ntiles > 0x7ffffff0ull) return GH_ERR_ARG;
 
   EncWorkspace ws;
   uint8_t* p = static_cast<uint8_t*>(d_workspace);
@@ -757,50 +506,28 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   const size_t used = size_t(p - static_cast<uint8_t*>(d_workspace)) + 8;
   GH_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, used, (cudaStream_t)stream));
 
-  static bool attrs_set = false;
-  if (!attrs_set) {  // both variants exceed the 48 KB a kernel gets without opting in
-    GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(EncSmem<4>))));
-    GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(EncSmem<2>))));
-    attrs_set = true;
-  }
+  // all of the SM's shared memory: the table's fixed window address decides the layout (see the kernel)
+  int dev = 0, smem_max = 0;
+  GH_CUDA_TRY(cudaGetDevice(&dev));
+  GH_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   const u64 out_word_cap = payload_cap / 4;
-  // persistent blocks: as many as are resident at once (shared memory allows 4 of variant 4, 3 of variant 2)
-  const bool short_codes = code->max_len <= 16;
-  int per_sm = 0;
-#ifndef GH_EMUL
-  if (short_codes) GH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<4>, kEncThreads, sizeof(EncSmem<4>)));
-  else GH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<2>, kEncThreads, sizeof(EncSmem<2>)));
-#endif
-  if (per_sm < 1) per_sm = kEncBlocksPerSm;
-  u64 blocks = u64(sm_count() > 0 ? sm_count() : 1) * u64(per_sm);
-  if (blocks > ntiles) blocks = ntiles;
-  const char* which = getenv("GH_ENCODE_KERNEL");
-  if (short_codes && which && which[0] == 'w') {  // experimental warp-independent kernel, see encode_warp_kernel
-    static bool warp_attr = false;
-    if (!warp_attr) {
-      GH_CUDA_TRY(cudaFuncSetAttribute(encode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(EncWarpSmem))));
-      warp_attr = true;
-    }
-    int wp = 0;
-#ifndef GH_EMUL
-    GH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wp, encode_warp_kernel, kEncThreads, sizeof(EncWarpSmem)));
-#endif
-    if (wp < 1) wp = GH_ENC_WARP_BLOCKS;
-    u64 wblocks = u64(sm_count() > 0 ? sm_count() : 1) * u64(wp);
-    if (wblocks > ntiles) wblocks = ntiles;
-    GH_LAUNCH(encode_warp_kernel, unsigned(wblocks), kEncThreads, sizeof(EncWarpSmem), stream, d_in, (u64)n, table, (u64)start_bit,
-              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
-  } else if (short_codes) {
-    GH_LAUNCH(encode_kernel<4>, unsigned(blocks), kEncThreads, sizeof(EncSmem<4>), stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
-              reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
+  // persistent: one CTA per SM, four tile-taking groups each
+  u64 blocks = u64(sm_count() > 0 ? sm_count() : 1);
+  const u64 want = (ntiles + kEncGroups - 1) / kEncGroups;
+  if (blocks > want) blocks = want;
+  if (long_codes) {
+    GH_LAUNCH(encode_kernel<1>, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, (u64)start_bit,
+              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws, u32(smem_max));
   } else {
-    GH_LAUNCH(encode_kernel<2>, unsigned(blocks), kEncThreads, sizeof(EncSmem<2>), stream, d_in, (u64)n, table, (u64)start_bit, append_eof,
-              reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws);
+    GH_LAUNCH(encode_kernel<2>, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, (u64)start_bit,
+              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws, u32(smem_max));
   }
   rc = check_launch();
   if (rc != GH_OK) return rc;
   if (ntiles > 1) {
-    GH_LAUNCH(encode_stitch_kernel, unsigned((ntiles + 255) / 256), 256, 0, stream, ntiles, (u64)start_bit,
+    GH_LAUNCH(encode_stitch_kernel, unsigned((ntiles + 255) / 256), 256, 0, stream, ntiles,
               reinterpret_cast<u32*>(d_payload), out_word_cap, ws);
     rc = check_launch();
   }

@@ -21,6 +21,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
   pthread_barrier_init(&g_block.bar, nullptr, nthreads);
   for (unsigned w = 0; w < nthreads / 32; w++) pthread_barrier_init(&g_block.warp_bar[w], nullptr, 32);
   g_block.vote.store(0);
+  for (int i = 0; i < 16; i++) g_block.named_state[i].store(0);
 
   // One pool of `nthreads` workers walks the grid: all workers execute block b, meet at a barrier, move on.
   // Blocks therefore run strictly one after another, in blockIdx order.
@@ -43,6 +44,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     });
   }
   for (auto& th : pool) th.join();
+  for (int i = 0; i < 16; i++)
+    if (g_block.named_state[i].load() == 2) pthread_barrier_destroy(&g_block.named_bar[i]);
   pthread_barrier_destroy(&g_block.bar);
   for (unsigned w = 0; w < nthreads / 32; w++) pthread_barrier_destroy(&g_block.warp_bar[w]);
 }

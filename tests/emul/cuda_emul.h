@@ -61,6 +61,9 @@ struct Block {
   pthread_barrier_t warp_bar[kMaxThreads / 32];
   uint64_t warp_xchg[kMaxThreads / 32][32];
   std::atomic<int> vote;
+  // named barriers (bar.sync id, count): initialised on first use in a launch, destroyed when the launch ends
+  pthread_barrier_t named_bar[16];
+  std::atomic<int> named_state[16];  // 0 = unused, 1 = being initialised, 2 = ready
   unsigned char dyn_smem[kMaxDynSmem] __attribute__((aligned(128)));
 };
 
@@ -75,6 +78,16 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 inline unsigned lane() { return t_threadIdx.x & 31u; }
 inline unsigned warp() { return t_threadIdx.x >> 5; }
 inline void warp_sync() { pthread_barrier_wait(&g_block.warp_bar[warp()]); }
+inline void named_barrier(unsigned id, unsigned count) {
+  int expected = 0;
+  if (g_block.named_state[id].compare_exchange_strong(expected, 1)) {
+    pthread_barrier_init(&g_block.named_bar[id], nullptr, count);
+    g_block.named_state[id].store(2);
+  } else {
+    while (g_block.named_state[id].load() != 2) std::this_thread::yield();
+  }
+  pthread_barrier_wait(&g_block.named_bar[id]);
+}
 
 template <class T>
 inline uint64_t to_bits(T v) {

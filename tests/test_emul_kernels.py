@@ -63,17 +63,13 @@ def test_emulated_near_fixed_length_code(emu, ctx, oracle):
     _roundtrip(emu, ctx, oracle, np.repeat(np.arange(256, dtype=np.uint8), 300).tobytes())
 
 
-def test_emulated_warp_independent_encoder(emu, ctx, oracle, monkeypatch):
-    """GH_ENCODE_KERNEL=warp selects the experimental encoder whose warps run their phases independently (short codes
-    only; long codes keep the default kernel): same bytes as the oracle on the golden inputs, on ragged sizes and
-    with every start phase of the sharding contract"""
+def test_emulated_encoder_phases_and_ragged_sizes(emu, ctx, oracle):
+    """the single-gather encoder: ragged sizes around the 32-byte slice, the 1 KiB warp row, the 8 KiB sub-tile and the
+    16 KiB tile (the slice that holds the last byte takes the codeword-by-codeword path), and every start phase of the
+    sharding contract"""
     import golden_huffman_b200 as gh
-    monkeypatch.setenv("GH_ENCODE_KERNEL", "warp")
-    for name in ["kat1_abracadabra", "kat2_a1000", "one_byte", "two_symbols", "text_small", "tile_exact_4096",
-                 "tile_plus1_4097", "kat3_allbytes512"]:
-        _roundtrip(emu, ctx, oracle, make_input(name))
     rng = np.random.default_rng(17)
-    for n in (5, 511, 2049, 16384, 16385, 40000):
+    for n in (5, 31, 32, 33, 511, 1023, 1024, 1025, 2049, 8191, 8192, 8193, 16384, 16385, 40000, 70001):
         _roundtrip(emu, ctx, oracle, np.minimum(rng.geometric(0.3, n), 255).astype(np.uint8).tobytes())
     data = make_input("text_small")
     n = len(data)
@@ -98,6 +94,21 @@ def test_emulated_warp_independent_encoder(emu, ctx, oracle, monkeypatch):
         lead = start_bit - first_word * 8
         assert not got[:lead].any()
         assert (got[lead:lead + total] == bits[:total]).all()
+
+
+def test_emulated_encoder_mixed_long_and_short_rows(emu, ctx, oracle):
+    """a code with lengths beyond 16 whose long codewords are rare: most warp rows take the four-codewords-per-chunk
+    path, the rows that contain a long codeword the slow one, inside the same tiles (8 KiB tiles for such codes)"""
+    f = [1, 2]
+    while len(f) < 24:
+        f.append(f[-1] + f[-2])
+    rng = np.random.default_rng(23)
+    body = np.repeat(np.arange(len(f), dtype=np.uint8), f)
+    rng.shuffle(body)
+    data = np.concatenate([np.full(20000, len(f) - 1, dtype=np.uint8), body, np.full(9000, len(f) - 2, dtype=np.uint8)])
+    rc, code = oracle.build_code(oracle.histogram(data.tobytes()))
+    assert rc == 0 and code.max_len > 16
+    _roundtrip(emu, ctx, oracle, data.tobytes())
 
 
 def test_emulated_kernels_random(emu, ctx, oracle):

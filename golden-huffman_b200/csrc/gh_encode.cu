@@ -6,31 +6,34 @@
 // input is not read a second time to learn the bit offsets, and every input byte is looked up ONCE).
 //
 // One persistent CTA of 1024 threads per SM, split into four independent GROUPS of 256 threads that share one
-// lookup table and synchronise among themselves with named barriers only. A group takes TILES of input from an
-// atomic ticket; a tile is kSubTiles sub-tiles of 8 KiB, a thread owns 32 consecutive bytes of a sub-tile.
+// lookup table and synchronise among themselves with named barriers only. A group takes 8 KiB TILES of input from
+// an atomic ticket; a thread owns 32 consecutive bytes of a tile. Per tile k of a group:
 //   1. gather + concatenate: per byte one PRMT (which forms the complete shared-memory address: the table has one
 //      64-bit entry (code << 16 | len, 2^len) per (byte value, lane) at 0x10000 + value * 256 + lane * 8, so the
 //      gathers of a warp can never conflict) and one LDS.64; four codewords are concatenated into a 64-bit chunk by
 //      multiply-adds with the powers of two (FMA pipe), the chunk length is the sum of the entries' low halves;
-//   2. per sub-tile: warp-shuffle scan of the thread bit counts, the eight warp totals cross one named barrier;
-//   3. staging: every chunk is OR-ed into the group's zeroed staging buffer at its TILE-relative bit position with
-//      shared-memory atomics (neighbouring chunks share words). This needs no global offset, so it runs before
-//      the tile's look-back has finished;
-//   4. the tile's bit count is published as (AGGREGATE | bits) as soon as the last sub-tile is counted; after
-//      staging, the group's first warp resolves the tile's start bit G by a decoupled look-back (Merrill & Garland)
-//      over 96 predecessors per L2 round trip -- with 32 per round trip the chain of prefixes, not the SMs, bounds a
-//      kernel this fast (16 KiB x 32 / 0.37 us = 1.4 TB/s) -- and publishes (PREFIX | end bit);
-//   5. copy-out: global word (G/32 + i) = funnel shift of staged words i-1, i by (G mod 32), byte-swapped to
-//      stream order, coalesced. The tile's first word, when shared with the previous tile, is NOT stored: its
-//      bits go to head[tile] and encode_stitch_kernel ORs them into the word the previous tile wrote -- every
-//      output word has exactly one writer per kernel, no global atomics on the payload. The last tile adds the
-//      1-padding (reference include/canonical_huff_encoder.cc:255-257); the staging buffer is cleared again.
+//   2. warp-shuffle scan of the thread bit counts, the eight warp totals cross the first named barrier; the tile's
+//      bit count is published at once as (AGGREGATE | bits);
+//   3. staging: every chunk is OR-ed into one of the group's THREE zeroed staging buffers at its tile-relative bit
+//      position with shared-memory atomics (neighbouring chunks share words); no global offset is needed for that;
+//   4. warp 0 then resolves the start bit G of the group's PREVIOUS tile k-1 by a decoupled look-back (Merrill &
+//      Garland) over 96 predecessors per L2 round trip, publishes (PREFIX | end bit) and draws the group's next tile;
+//   5. meanwhile warps 1-7 copy out tile k-2, whose G has been known since the last iteration: global word (G/32 + i) =
+//      funnel shift of staged words i-1, i by (G mod 32), byte-swapped to stream order, coalesced; the second barrier
+//      of the iteration then frees that buffer (cleared; re-used by tile k+1).
+//      A tile's count is thus published a whole tile period before anybody asks for it, and nobody waits for a
+//      look-back. With look-back and copy-out right after staging, the groups ran in lock step with the slowest SM:
+//      38-47 % of the warp samples sat at the barrier behind the look-back (profiles/r2_enc_notes.md).
+//      The tile's first word, when shared with the previous tile, is NOT stored: its bits go to head[tile] and
+//      encode_stitch_kernel ORs them into the word the previous tile wrote -- every output word has exactly one
+//      writer per kernel, no global atomics on the payload. The last tile adds the 1-padding (reference
+//      include/canonical_huff_encoder.cc:255-257).
 // Codewords longer than 16 bits cannot take part in step 1 (four of them do not fit a 64-bit chunk). Their table
-// entries carry a flag that survives the length sum; a warp whose 1 KiB slice of the sub-tile contains one -- or the
-// ragged end of the input, or the byte that the end mark follows -- handles that slice codeword by codeword
-// (count_slow / stage_slow). A Huffman code gives such lengths only to symbols rarer than 2^-16 or so.
-// When the code has such codewords, tiles are one sub-tile (8 KiB), so that even a tile of nothing but 32-bit
-// codewords fits the staging buffer.
+// entries carry a flag that survives the length sum; a warp whose 1 KiB row of the tile contains one -- or the ragged
+// end of the input, or the byte that the end mark follows -- handles that row codeword by codeword (count_slow /
+// stage_slow). A Huffman code gives such lengths only to symbols rarer than 2^-16 or so. A tile whose bits do not fit
+// one staging buffer (more than ~12 bits per byte on average) drains the group's pipeline, is staged across all three
+// buffers and copied out at once (the "big tile" path).
 #include "gh_common.cuh"
 
 namespace gh {
@@ -40,30 +43,32 @@ constexpr int kEncGroups = 4;
 constexpr int kEncThreads = kEncGroupThreads * kEncGroups;  // one CTA per SM
 constexpr int kEncGroupWarps = kEncGroupThreads / 32;
 constexpr int kEncBytesPerThread = 32;
-constexpr int kEncChunks = kEncBytesPerThread / 4;                        // 64-bit chunks of four codewords
-constexpr int kEncSubTileBytes = kEncGroupThreads * kEncBytesPerThread;  // 8 KiB
-constexpr int kEncRowBytes = 32 * kEncBytesPerThread;                    // a warp's slice of a sub-tile
-constexpr int kEncMaxSubTiles = 2;
-constexpr int kEncMinTileBytes = kEncSubTileBytes;
-constexpr int kEncLookDepth = 3;    // predecessors per lane and look-back round
+constexpr int kEncChunks = kEncBytesPerThread / 4;                    // 64-bit chunks of four codewords
+constexpr int kEncTileBytes = kEncGroupThreads * kEncBytesPerThread;  // 8 KiB
+constexpr int kEncRowBytes = 32 * kEncBytesPerThread;                 // a warp's row of a tile
+constexpr int kEncLookDepth = 3;       // predecessors per lane and look-back round
 constexpr u32 kEncLongFlag = 0x1000u;  // in the low half of a table entry: codeword longer than 16 bits
 
-// staging buffer of a group: worst case 16384 codewords of 16 bits, or 8192 of 32 bits, plus the end mark; four zero
-// words in front (staging ORs up to two words below a chunk's last word, copy-out reads word -1; 16-byte aligned
-// clearing) and slack behind
+// Staging of a group: four zero words in front (staging ORs up to two words below a chunk's last word, copy-out
+// reads word -1; 16-byte aligned clearing), then three buffers of 3068 words (a tile of up to 98048 bits, ~12 bits
+// per byte; the last four words of a buffer stay zero). A tile of 8192 codewords of 32 bits + the end mark fits the
+// three together.
 constexpr int kEncStageFront = 4;
-constexpr int kEncStageWords = kEncMaxSubTiles * kEncSubTileBytes * 16 / 32 + 2 + 6;
-constexpr int kEncStageBytes = (kEncStageFront + kEncStageWords) * 4;
+constexpr int kEncBufs = 3;
+constexpr int kEncBufWords = 3068;
+constexpr u32 kEncBufBits = u32(kEncBufWords - 4) * 32u;  // a tile with more bits than this takes the big-tile path
+constexpr int kEncStageBytes = (kEncStageFront + kEncBufs * kEncBufWords) * 4;
+static_assert(kEncBufs * kEncBufWords * 32 >= kEncTileBytes * 32 + 32 + 128, "a tile of 32-bit codewords must fit the three buffers");
 
-// Shared memory. The replicated table must sit at the shared-window address 0x10000 so that a single PRMT can
-// assemble an entry's address from (0x01, byte value, lane * 8); the rest is laid out around it.
-constexpr u32 kEncLutAddr = 0x10000u;
+// Shared memory. The replicated table must sit at a 64 KiB-aligned shared-window address so that a single PRMT can
+// assemble an entry's address from (0x02, byte value, lane * 8); the groups' staging areas are laid out around it.
+constexpr u32 kEncLutAddr = 0x20000u;
 constexpr u32 kEncLutBytes = 256u * 256u;
 struct EncGroupCtl {
-  u32 wtot[2][kEncGroupWarps];  // warp totals of a sub-tile, double-buffered
+  u32 wtot[kEncGroupWarps];  // warp totals of the tile being counted
   u64 tile_start;
   u32 next_tile;
-  u32 pad[3];
+  u32 pad[5];
 };
 struct EncLowSmem {  // at the start of dynamic shared memory
   EncGroupCtl ctl[kEncGroups];
@@ -80,7 +85,7 @@ struct EncWorkspace {
   u32* ticket;      // tile dispenser (tiles are handed out in the order groups ask for them)
 };
 
-__host__ __device__ inline u64 enc_num_tiles(u64 n, u32 tile_bytes) { return (n + tile_bytes - 1) / tile_bytes; }
+__host__ __device__ inline u64 enc_num_tiles(u64 n) { return (n + kEncTileBytes - 1) / kEncTileBytes; }
 
 // ---- named barrier of one group -----------------------------------------------------------------------------------
 __device__ __forceinline__ void group_barrier(unsigned group) {
@@ -100,8 +105,8 @@ __device__ __forceinline__ uint2 enc_lut_entry(enc_lut_t lut_lane, u32 word, int
 #else
 typedef u32 enc_lut_t;  // kEncLutAddr | lane * 8
 __device__ __forceinline__ uint2 enc_lut_entry(enc_lut_t lut_lane, u32 word, int k) {
-  // address = 0x00 0x01 <byte k of word> <lane * 8>: bytes 3 and 2 and 0 from lut_lane, byte 1 from the input word
-  const u32 addr = __byte_perm(word, lut_lane, 0x7604u | (u32(k) << 4));
+  // address = 0x00 0x02 <byte k of word> <lane * 8>: bytes 3 and 2 and 0 from lut_lane, byte 1 from the input word
+  const u32 addr = __byte_perm(word, lut_lane, 0x7604u | (u32(k) << 4));  // bytes 3, 2 (0x0002) and 0 of lut_lane
   uint2 v;
   asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
@@ -175,16 +180,12 @@ __device__ __noinline__ u32 stage_slow(enc_stage_t stage, u32 pos, const uint2* 
   return pos;
 }
 
-// Decoupled look-back by one whole warp. The tile's own count was published as an AGGREGATE before (tiles > 0);
+// Decoupled look-back by one whole warp. The tile's own count was published before (AGGREGATE; tile 0: PREFIX);
 // this adds up the predecessors' counts back to the nearest tile that already knows its start, publishes this
 // tile's end bit and returns its start bit (all 32 lanes must call it together).
 __device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 tile, u32 tile_bits, u64 start_bit, unsigned lane) {
-  u64 exclusive = start_bit;
-  if (tile == 0) {
-    if (lane == 0) st_volatile_u64(ws.tile_state, kFlagPrefix | (start_bit + tile_bits));
-    return exclusive;
-  }
-  exclusive = 0;
+  if (tile == 0) return start_bit;  // tile 0 published its PREFIX when it was counted
+  u64 exclusive = 0;
   long long look = (long long)tile - 1;
   bool done = false;
   while (!done) {
@@ -219,35 +220,74 @@ __device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 t
   return exclusive;
 }
 
-template <int kSubTiles>
+// copy-out of one staged tile: `nthr` threads (this one is number `t`) store the words of the tile that starts at
+// global bit G, reading the bit string staged at `stage`
+__device__ __forceinline__ void enc_copy_out(enc_stage_t stage, u32 tile_bits, u64 tile, u64 G, bool last_tile, int append_eof,
+                                             u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out,
+                                             const EncWorkspace& ws, u32 t, u32 nthr) {
+  const u32 phase = u32(G) & 31u;
+  const u64 end_bit = G + tile_bits;
+  const u64 word0 = G >> 5;
+  const u32 nwords = (phase + tile_bits + 31u) >> 5;  // tile_bits > 0: every tile holds at least one codeword
+  if (last_tile && t == 0 && end_bit_out) *end_bit_out = end_bit;
+  u32* const dst = out_words + word0;
+  const u64 room = out_word_cap > word0 ? out_word_cap - word0 : 0;
+  const u32 lim = u64(nwords - 1u) < room ? nwords - 1u : u32(room);  // interior words: 1 .. nwords - 2
+  for (u32 i = t + 1u; i < lim; i += nthr)
+    dst[i] = be32(__funnelshift_r(enc_stage_ld(stage, i, 0), enc_stage_ld(stage, i, -1), phase));
+  // first and last word of the tile
+  if (t < 2u && (t == 0 || nwords > 1u)) {
+    const u32 i = t == 0 ? 0u : nwords - 1u;
+    u32 v = __funnelshift_r(enc_stage_ld(stage, i, 0), enc_stage_ld(stage, i, -1), phase);
+    if (append_eof && last_tile && i == nwords - 1u) {
+      const u32 pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s up to the byte boundary
+      if (pad) v |= ((1u << pad) - 1u) << (32u - (u32(end_bit & 31) + pad));
+    }
+    if (i == 0 && tile > 0 && phase != 0) ws.head[tile] = v;  // shared with the previous tile: stitched later
+    else if (u64(i) < room) dst[i] = be32(v);
+  }
+}
+
+__device__ __forceinline__ void enc_clear(u32* buf, u32 tile_bits, u32 t) {
+  uint4* const z = reinterpret_cast<uint4*>(buf);
+  for (u32 i = t; i < (tile_bits >> 7) + 1u; i += kEncGroupThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+struct EncPending {  // a staged tile of the group (group-uniform values)
+  bool valid;
+  u32 bits, buf;
+  u64 tile, G;
+};
+
 __global__ void __launch_bounds__(kEncThreads, 1)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
               u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws,
               u32 smem_bytes) {
-  constexpr u32 kTileBytes = u32(kSubTiles) * kEncSubTileBytes;
   GH_DYNAMIC_SMEM(smem_raw);
   const unsigned group = threadIdx.x / kEncGroupThreads, tg = threadIdx.x % kEncGroupThreads;
   const unsigned lane = tg & 31, wg = tg >> 5;
 
-  // ---- carve shared memory around the table's fixed address ------------------------------------------------------
+  // ---- carve shared memory around the table's fixed address: staging areas below it first, then above it ----------
   EncLowSmem& low = *reinterpret_cast<EncLowSmem*>(smem_raw);
+  constexpr u32 kLowBytes = (u32(sizeof(EncLowSmem)) + 15u) & ~15u;
 #ifdef GH_EMUL
-  const u32 lut_off = kEncLutAddr - 0x400u;
+  const u32 smem_base = 0x400u;
 #else
   const u32 smem_base = u32(__cvta_generic_to_shared(smem_raw));
+#endif
   const u32 lut_off = kEncLutAddr - smem_base;
-  if (smem_base > kEncLutAddr - u32(sizeof(EncLowSmem)) - u32(kEncStageBytes) - 16u ||
-      lut_off + kEncLutBytes + 3u * u32(kEncStageBytes) > smem_bytes)
+  const u32 below = (lut_off - kLowBytes) / u32(kEncStageBytes);  // groups that fit between the tables and the big table
+  const u32 stage_off = group < below ? kLowBytes + group * u32(kEncStageBytes)
+                                      : lut_off + kEncLutBytes + (group - below) * u32(kEncStageBytes);
+#ifndef GH_EMUL
+  if (smem_base + kLowBytes > kEncLutAddr || (smem_base & 15u) ||
+      lut_off + kEncLutBytes + (u32(kEncGroups) - (below < u32(kEncGroups) ? below : u32(kEncGroups))) * u32(kEncStageBytes) > smem_bytes)
     __trap();  // the launch did not provide the window this layout needs
 #endif
   (void)smem_bytes;
   unsigned char* const lut_ptr = smem_raw + lut_off;
-  // group 0 stages below the table, groups 1..3 above it
-  u32* const stage_base = group == 0
-                              ? reinterpret_cast<u32*>(smem_raw + ((sizeof(EncLowSmem) + 15) & ~size_t(15)))
-                              : reinterpret_cast<u32*>(lut_ptr + kEncLutBytes + size_t(group - 1) * kEncStageBytes);
-  u32* const stage_ptr = stage_base + kEncStageFront;
-  const enc_stage_t stage = enc_stage_handle(stage_ptr);
+  u32* const stage_base = reinterpret_cast<u32*>(smem_raw + stage_off);
+  u32* const buf_ptr0 = stage_base + kEncStageFront;
   EncGroupCtl& ctl = low.ctl[group];
 
   // ---- tables (once per CTA) ---------------------------------------------------------------------------------------
@@ -262,7 +302,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   }
   for (unsigned i = threadIdx.x; i < unsigned(GH_NSYM); i += kEncThreads)
     low.long_table[i] = make_uint2(table.codeword[i], u32(table.length[i]));
-  for (unsigned i = tg; i < unsigned(kEncStageFront + kEncStageWords); i += kEncGroupThreads) stage_base[i] = 0;
+  for (unsigned i = tg; i < unsigned(kEncStageFront + kEncBufs * kEncBufWords); i += kEncGroupThreads) stage_base[i] = 0;
   if (tg == 0) ctl.next_tile = atomicAdd(ws.ticket, 1u);
   __syncthreads();
 #ifdef GH_EMUL
@@ -271,157 +311,161 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   const enc_lut_t lut_lane = kEncLutAddr | (lane * 8u);
 #endif
   const uint2* const long_table = low.long_table;
-  const u64 ntiles = enc_num_tiles(n, kTileBytes);
+  const u64 ntiles = enc_num_tiles(n);
   const bool aligned32 = (reinterpret_cast<uintptr_t>(in) & 31) == 0;
   const u32 eof_code = table.codeword[GH_EOF_SYMBOL];
   const u32 eof_len = append_eof ? u32(table.length[GH_EOF_SYMBOL]) : 0u;
-  const u32 toff = tg * kEncBytesPerThread;           // this thread's slice inside a sub-tile
-  const u32 roff = (tg & ~31u) * kEncBytesPerThread;  // its warp's row
-  u32 wpar = 0;  // slot of wtot the next sub-tile uses
+  const u32 off = tg * kEncBytesPerThread;           // this thread's slice inside a tile
+  const u32 row = (tg & ~31u) * kEncBytesPerThread;  // its warp's row
+
+  u32 cur = 0;     // buffer the next tile is staged into
+  EncPending A;    // staged, start bit not resolved yet (the previous tile)
+  EncPending B;    // staged and resolved, awaits its copy-out (the tile before that)
+  A.valid = B.valid = false;
+  A.bits = B.bits = A.buf = B.buf = 0;
+  A.tile = B.tile = A.G = B.G = 0;
+
+  auto copy_out = [&](const EncPending& p, u32 t, u32 nthr) {
+    enc_copy_out(enc_stage_handle(buf_ptr0 + p.buf * kEncBufWords), p.bits, p.tile, p.G, p.tile + 1 == ntiles, append_eof,
+                 out_words, out_word_cap, end_bit_out, ws, t, nthr);
+  };
+  // completes the pending tiles with the whole group (big-tile path and the end of the loop)
+  auto drain = [&]() {
+    group_barrier(group);  // every thread has taken B.G and the next tile's number from ctl (they are rewritten below)
+    if (B.valid) copy_out(B, tg, kEncGroupThreads);
+    if (A.valid && wg == 0) {
+      const u64 g = tile_start_lookback(ws, A.tile, A.bits, start_bit, lane);
+      if (lane == 0) ctl.tile_start = g;
+    }
+    group_barrier(group);
+    if (B.valid) enc_clear(buf_ptr0 + B.buf * kEncBufWords, B.bits, tg);
+    if (A.valid) {
+      A.G = ctl.tile_start;
+      copy_out(A, tg, kEncGroupThreads);
+      group_barrier(group);
+      enc_clear(buf_ptr0 + A.buf * kEncBufWords, A.bits, tg);
+    }
+    A.valid = B.valid = false;
+  };
 
   u64 tile = ctl.next_tile;
   while (tile < ntiles) {
-    const u64 tile_base = tile * kTileBytes;
+    const u64 tile_base = tile * kEncTileBytes;
     const uint8_t* const tin = in + tile_base;
     const u64 left = n - tile_base;
-    const u32 rem = left < u64(kTileBytes) ? u32(left) : kTileBytes;  // bytes of this tile (short only for the last one)
+    const u32 rem = left < u64(kEncTileBytes) ? u32(left) : u32(kEncTileBytes);  // short only for the last tile
     const bool last_tile = (tile + 1 == ntiles);
-    // all of the tile's loads up front
-    EncVec vec[kSubTiles];
+    EncVec vec;
+    if (off + kEncBytesPerThread <= rem) {
+      vec = enc_load_vec(tin + off, aligned32);
+    } else {
 #pragma unroll
-    for (int j = 0; j < kSubTiles; ++j) {
-      const u32 off = u32(j) * kEncSubTileBytes + toff;
-      if (off + kEncBytesPerThread <= rem) {
-        vec[j] = enc_load_vec(tin + off, aligned32);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) vec[j].w[k] = 0;
-      }
+      for (int k = 0; k < 8; ++k) vec.w[k] = 0;
     }
-    u32 sub_base = 0;  // bits of this tile in earlier sub-tiles
-    u32 tile_bits = 0;
+    // ---- 1. gather + concatenate -----------------------------------------------------------------------------
+    u32 c_lo[kEncChunks], c_hi[kEncChunks], c_end[kEncChunks];
+    u32 bits = 0, flags = 0;
 #pragma unroll
-    for (int j = 0; j < kSubTiles; ++j) {
-      const u32 off = u32(j) * kEncSubTileBytes + toff;
-      const u32 row = u32(j) * kEncSubTileBytes + roff;
-      // ---- 1. gather + concatenate ---------------------------------------------------------------------------
-      u32 c_lo[kEncChunks], c_hi[kEncChunks], c_end[kEncChunks];
-      u32 bits = 0, flags = 0;
+    for (int c = 0; c < kEncChunks; ++c) {
+      const u32 word = vec.w[c];
+      const uint2 e0 = enc_lut_entry(lut_lane, word, 0);
+      const uint2 e1 = enc_lut_entry(lut_lane, word, 1);
+      const uint2 e2 = enc_lut_entry(lut_lane, word, 2);
+      const uint2 e3 = enc_lut_entry(lut_lane, word, 3);
+      // acc = ((c0 * 2^l1 + c1) * 2^l2 * 2^l3) + (c2 * 2^l3 + c3): products on the FMA pipe; the additions cannot
+      // carry because the products' low bits are zero
+      const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
+      const u32 a23 = __umulhi(e2.x, 1u << 16) * e3.y + __umulhi(e3.x, 1u << 16);  // <= 32 bits
+      const u64 t = u64(a01) * e2.y;                                               // <= 48 bits
+      const u64 acc = t * e3.y + a23;
+      c_lo[c] = u32(acc);
+      c_hi[c] = u32(acc >> 32);
+      const u32 l = (e0.x + e1.x + e2.x + e3.x) & 0xffffu;  // lengths (and long-codeword flags) add up in the low half
+      flags |= l;
+      bits += l;
+      c_end[c] = bits;  // end of this chunk relative to the thread's first bit
+    }
+    // rows that need the slow path: a long codeword, the ragged end, or the byte the end mark follows
+    const bool row_live = row < rem;
+    const bool row_end = last_tile && row + kEncRowBytes >= rem;
+    bool slow = false;
+    int cnt = 0;
+    bool owns_end = false;
+    if (row_live) {
+      slow = row_end || __any_sync(0xffffffffu, (flags & 0xf000u) != 0u);
+      if (slow) {
+        cnt = off >= rem ? 0 : (rem - off < u32(kEncBytesPerThread) ? int(rem - off) : kEncBytesPerThread);
+        bits = count_slow(long_table, tin + off, cnt);
+        owns_end = last_tile && cnt > 0 && off + u32(cnt) == rem;
+        if (owns_end) bits += eof_len;
+      }
+    } else {
+      bits = 0;
+    }
+    // ---- 2. scan ---------------------------------------------------------------------------------------------
+    const u32 incl = warp_inclusive_scan(bits, lane);
+    if (lane == 31) ctl.wtot[wg] = incl;
+    group_barrier(group);  // (a) warp totals; every clear of the previous iteration is done
+    u32 wprefix, tile_bits;
+    {
+      // the eight warp totals, scanned by every warp for itself
+      u32 v = lane < u32(kEncGroupWarps) ? ctl.wtot[lane] : 0u;
 #pragma unroll
-      for (int c = 0; c < kEncChunks; ++c) {
-        const u32 word = vec[j].w[c];
-        const uint2 e0 = enc_lut_entry(lut_lane, word, 0);
-        const uint2 e1 = enc_lut_entry(lut_lane, word, 1);
-        const uint2 e2 = enc_lut_entry(lut_lane, word, 2);
-        const uint2 e3 = enc_lut_entry(lut_lane, word, 3);
-        // acc = ((c0 * 2^l1 + c1) * 2^l2 * 2^l3) + (c2 * 2^l3 + c3): products on the FMA pipe; the additions cannot
-        // carry because the products' low bits are zero
-        const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
-        const u32 a23 = __umulhi(e2.x, 1u << 16) * e3.y + __umulhi(e3.x, 1u << 16);  // <= 32 bits
-        const u64 t = u64(a01) * e2.y;                                               // <= 48 bits
-        const u64 acc = t * e3.y + a23;
-        c_lo[c] = u32(acc);
-        c_hi[c] = u32(acc >> 32);
-        const u32 l = (e0.x + e1.x + e2.x + e3.x) & 0xffffu;  // lengths (and long-codeword flags) add up in the low half
-        flags |= l;
-        bits += l;
-        c_end[c] = bits;  // end of this chunk relative to the thread's first bit
+      for (int d = 1; d < kEncGroupWarps; d <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= unsigned(d)) v += up;
       }
-      // slices that need the slow path: a long codeword, the ragged end, or the byte the end mark follows
-      const bool row_live = row < rem;
-      const bool row_end = last_tile && row + kEncRowBytes >= rem;
-      bool slow = false;
-      int cnt = 0;
-      bool owns_end = false;
-      if (row_live) {
-        slow = row_end || __any_sync(0xffffffffu, (flags & 0xf000u) != 0u);
-        if (slow) {
-          cnt = off >= rem ? 0 : (rem - off < u32(kEncBytesPerThread) ? int(rem - off) : kEncBytesPerThread);
-          bits = count_slow(long_table, tin + off, cnt);
-          owns_end = last_tile && cnt > 0 && off + u32(cnt) == rem;
-          if (owns_end) bits += eof_len;
-        }
-      } else {
-        bits = 0;
-      }
-      // ---- 2. scan ---------------------------------------------------------------------------------------------
-      const u32 incl = warp_inclusive_scan(bits, lane);
-      if (lane == 31) ctl.wtot[wpar][wg] = incl;
+      tile_bits = __shfl_sync(0xffffffffu, v, kEncGroupWarps - 1);
+      wprefix = __shfl_sync(0xffffffffu, v, int(wg)) - __shfl_sync(0xffffffffu, incl, 31);
+    }
+    // the tile's count is known to everybody a whole tile period before its own look-back runs
+    if (tg == 0) st_volatile_u64(ws.tile_state + tile, tile > 0 ? (kFlagAggregate | u64(tile_bits)) : (kFlagPrefix | (start_bit + tile_bits)));
+    const u32 pos = wprefix + incl - bits;
+    const bool big = tile_bits > kEncBufBits;  // group-uniform
+    if (big) {
+      // rare: the tile needs all three buffers. The pending tiles leave first, then this one, at once.
+      drain();
       group_barrier(group);
-      u32 wprefix, sub_bits;
-      {
-        // the eight warp totals, scanned by every warp for itself
-        u32 v = lane < u32(kEncGroupWarps) ? ctl.wtot[wpar][lane] : 0u;
-#pragma unroll
-        for (int d = 1; d < kEncGroupWarps; d <<= 1) {
-          const u32 up = __shfl_up_sync(0xffffffffu, v, d);
-          if (lane >= unsigned(d)) v += up;
-        }
-        sub_bits = __shfl_sync(0xffffffffu, v, kEncGroupWarps - 1);
-        const u32 mine = __shfl_sync(0xffffffffu, v, int(wg));
-        wprefix = mine - __shfl_sync(0xffffffffu, incl, 31);
-      }
-      wpar ^= 1;
-      if (j == kSubTiles - 1) {
-        tile_bits = sub_base + sub_bits;
-        if (tg == 0 && tile > 0) st_volatile_u64(ws.tile_state + tile, kFlagAggregate | u64(tile_bits));
-      }
-      // ---- 3. staging at tile-relative positions ----------------------------------------------------------------
-      const u32 pos = sub_base + wprefix + incl - bits;
-      if (!slow) {
-        if (row_live) {
-#pragma unroll
-          for (int c = 0; c < kEncChunks; ++c) stage_chunk(stage, pos + c_end[c], c_lo[c], c_hi[c]);
-        }
-      } else {
-        const u32 p2 = stage_slow(stage, pos, long_table, tin + off, cnt);
-        if (owns_end && eof_len) stage_chunk(stage, p2 + eof_len, eof_code, 0u);
-      }
-      sub_base += sub_bits;
+      cur = 0;
     }
-
-    // ---- 4. the tile's start bit ---------------------------------------------------------------------------------
+    // ---- 3. staging at tile-relative positions -------------------------------------------------------------------
+    const enc_stage_t stage = enc_stage_handle(buf_ptr0 + cur * kEncBufWords);
+    if (!slow) {
+      if (row_live) {
+#pragma unroll
+        for (int c = 0; c < kEncChunks; ++c) stage_chunk(stage, pos + c_end[c], c_lo[c], c_hi[c]);
+      }
+    } else {
+      const u32 p2 = stage_slow(stage, pos, long_table, tin + off, cnt);
+      if (owns_end && eof_len) stage_chunk(stage, p2 + eof_len, eof_code, 0u);
+    }
+    // ---- 4. + 5. warp 0: the previous tile's start bit, the next tile's number; the others: copy-out of tile k-2 -----
     if (wg == 0) {
-      const u64 exclusive = tile_start_lookback(ws, tile, tile_bits, start_bit, lane);
-      if (lane == 0) ctl.tile_start = exclusive;
-    }
-    group_barrier(group);  // staging complete, tile start known
-    // The next tile is drawn only now: a tile number that is held while its holder still waits for its own
-    // predecessors delays every later tile (they need this one's bit count), so it is held as briefly as possible.
-    if (tg == 0) ctl.next_tile = atomicAdd(ws.ticket, 1u);
-
-    // ---- 5. copy-out ------------------------------------------------------------------------------------------------
-    const u64 G = ctl.tile_start;
-    const u32 phase = u32(G) & 31u;
-    const u64 end_bit = G + tile_bits;
-    const u64 word0 = G >> 5;
-    const u32 nwords = (phase + tile_bits + 31u) >> 5;  // tile_bits > 0: every tile holds at least one codeword
-    if (last_tile && tg == 0 && end_bit_out) *end_bit_out = end_bit;
-    {
-      u32* const dst = out_words + word0;
-      const u64 room = out_word_cap > word0 ? out_word_cap - word0 : 0;
-      const u32 lim = u64(nwords - 1u) < room ? nwords - 1u : u32(room);  // interior words: 1 .. nwords - 2
-      for (u32 i = tg + 1u; i < lim; i += kEncGroupThreads)
-        dst[i] = be32(__funnelshift_r(enc_stage_ld(stage, i, 0), enc_stage_ld(stage, i, -1), phase));
-      // first and last word of the tile
-      if (tg < 2u && (tg == 0 || nwords > 1u)) {
-        const u32 i = tg == 0 ? 0u : nwords - 1u;
-        u32 v = __funnelshift_r(enc_stage_ld(stage, i, 0), enc_stage_ld(stage, i, -1), phase);
-        if (append_eof && last_tile && i == nwords - 1u) {
-          const u32 pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s up to the byte boundary
-          if (pad) v |= ((1u << pad) - 1u) << (32u - (u32(end_bit & 31) + pad));
-        }
-        if (i == 0 && tile > 0 && phase != 0) ws.head[tile] = v;  // shared with the previous tile: stitched later
-        else if (u64(i) < room) dst[i] = be32(v);
+      u64 g = 0;
+      if (A.valid) g = tile_start_lookback(ws, A.tile, A.bits, start_bit, lane);
+      if (lane == 0) {
+        ctl.tile_start = g;
+        ctl.next_tile = atomicAdd(ws.ticket, 1u);
       }
+    } else if (B.valid) {
+      copy_out(B, tg - 32u, kEncGroupThreads - 32u);
     }
-    group_barrier(group);  // every staged word has been read, the next tile's number is there
+    group_barrier(group);  // (b) tile k staged, G of tile k-1 and the next tile's number known, tile k-2 read
+    if (B.valid) enc_clear(buf_ptr0 + B.buf * kEncBufWords, B.bits, tg);
+    B = A;
+    B.G = ctl.tile_start;
+    A.valid = true;
+    A.bits = tile_bits;
+    A.buf = cur;
+    A.tile = tile;
+    cur = cur == u32(kEncBufs - 1) ? 0u : cur + 1u;
+    if (big) {
+      drain();  // B is invalid here; A (this tile, from buffer 0 across all three) is resolved and copied out
+      cur = 0;
+    }
     tile = ctl.next_tile;
-    {
-      uint4* const z = reinterpret_cast<uint4*>(stage_ptr);
-      for (u32 i = tg; i < (tile_bits >> 7) + 1u; i += kEncGroupThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
   }
+  drain();
 }
 
 // Second kernel: OR each tile's deferred head bits into the word its predecessor stored.
@@ -447,7 +491,7 @@ encode_stitch_kernel(u64 ntiles, u32* __restrict__ out_words, u64 out_word_cap, 
 }
 
 inline size_t enc_ws_bytes(u64 n) {
-  const u64 nt = enc_num_tiles(n, kEncMinTileBytes) + 1;
+  const u64 nt = enc_num_tiles(n) + 1;
   return size_t(nt * 8 + ((nt * 4 + 7) / 8) * 8 + 256);
 }
 
@@ -488,12 +532,7 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   EncodeTable table;
   int rc = build_encode_table(code, &table);
   if (rc != GH_OK) return rc;
-  // codewords of byte values longer than 16 bits take the slow path and halve the tile (the end mark's own length
-  // does not matter: it is staged once, by the slow path)
-  bool long_codes = false;
-  for (int s = 0; s < 256; ++s) long_codes = long_codes || table.length[s] > 16;
-  const u32 tile_bytes = long_codes ? kEncSubTileBytes : 2 * kEncSubTileBytes;
-  const u64 ntiles = enc_num_tiles(n, tile_bytes);
+  const u64 ntiles = enc_num_tiles(n);
   if (ntiles > 0x7ffffff0ull) return GH_ERR_ARG;
 
   EncWorkspace ws;
@@ -510,20 +549,14 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   int dev = 0, smem_max = 0;
   GH_CUDA_TRY(cudaGetDevice(&dev));
   GH_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   const u64 out_word_cap = payload_cap / 4;
   // persistent: one CTA per SM, four tile-taking groups each
   u64 blocks = u64(sm_count() > 0 ? sm_count() : 1);
   const u64 want = (ntiles + kEncGroups - 1) / kEncGroups;
   if (blocks > want) blocks = want;
-  if (long_codes) {
-    GH_LAUNCH(encode_kernel<1>, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, (u64)start_bit,
-              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws, u32(smem_max));
-  } else {
-    GH_LAUNCH(encode_kernel<2>, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, (u64)start_bit,
-              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws, u32(smem_max));
-  }
+  GH_LAUNCH(encode_kernel, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, (u64)start_bit,
+            append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws, u32(smem_max));
   rc = check_launch();
   if (rc != GH_OK) return rc;
   if (ntiles > 1) {

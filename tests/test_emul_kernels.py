@@ -111,6 +111,39 @@ def test_emulated_encoder_mixed_long_and_short_rows(emu, ctx, oracle):
     _roundtrip(emu, ctx, oracle, data.tobytes())
 
 
+def _big_tile_input(seed=29):
+    """240 byte values that occur 36 times each below a ladder of nine values whose counts double (9000, 18000, ...):
+    the rare values sit nine levels down the code tree and get 16- and 17-bit codewords. All of them are packed into
+    the second 8 KiB tile, which therefore needs more than 16 bits per byte, i.e. both staging buffers of its group."""
+    rng = np.random.default_rng(seed)
+    rare = np.repeat(np.arange(10, 250, dtype=np.uint8), 36)
+    rng.shuffle(rare)
+    ladder = np.repeat(np.arange(9, dtype=np.uint8), [9000 << i for i in range(9)])
+    rng.shuffle(ladder)
+    return np.concatenate([ladder[:8192], rare, ladder[8192:]])
+
+
+def test_emulated_encoder_big_tile(emu, oracle):
+    import golden_huffman_b200 as gh
+    data = _big_tile_input()
+    n = data.size
+    raw = data.tobytes()
+    rc, code = oracle.build_code(oracle.histogram(raw))
+    assert rc == 0 and max(code.length[b] for b in range(10, 250)) > 16
+    assert sum(code.length[b] for b in data[8192:16384]) > 8192 * 16
+    _, want = oracle.encode_payload(raw, code)
+    pcode = gh.GhCode.from_buffer_copy(bytes(code))
+    din = aligned(n + 32)
+    din[:n] = data
+    cap = emu.encode_payload_capacity(n, pcode, 0)
+    out = aligned(cap)
+    ws = aligned(emu.encode_workspace_bytes(n) + 256)
+    end = aligned(1, np.uint64)
+    emu.encode(din.ctypes.data, n, pcode, out.ctypes.data, cap, ws.ctypes.data, ws.size, start_bit=0, append_eof=True,
+               d_end_bit=end.ctypes.data)
+    assert out[:len(want)].tobytes() == want
+
+
 def test_emulated_kernels_random(emu, ctx, oracle):
     rng = np.random.default_rng(3)
     sizes = [3, 17, 4095, 8193, 30000]

@@ -89,6 +89,17 @@ __device__ __forceinline__ void ldg128_into(uint4& dst, const uint4* p) {
 #endif
 }
 
+// Bulk prefetch of `bytes` (multiple of 16, 16-byte aligned address) from DRAM into L2: one instruction, no registers,
+// nothing to wait for (UBLKPF). A hint only.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, u32 bytes) {
+#ifdef GH_EMUL
+  (void)gptr;
+  (void)bytes;
+#else
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+#endif
+}
+
 // Single-word flag|value messages between thread blocks: relaxed, GPU scope (served by L2, no system-scope
 // round trip). One 64-bit word carries flag and value together, so no fence is needed around them.
 __device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {

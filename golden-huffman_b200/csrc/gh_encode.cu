@@ -9,9 +9,9 @@
 // lookup table and synchronise among themselves with named barriers only. A group takes 8 KiB TILES of input from
 // an atomic ticket; a thread owns 32 consecutive bytes of a tile. Per tile k of a group:
 //   1. gather + concatenate: per byte one PRMT (which forms the complete shared-memory address: the table has one
-//      64-bit entry (code << 16 | len, 2^len) per (byte value, lane) at 0x10000 + value * 256 + lane * 8, so the
-//      gathers of a warp can never conflict) and one LDS.64; four codewords are concatenated into a 64-bit chunk by
-//      multiply-adds with the powers of two (FMA pipe), the chunk length is the sum of the entries' low halves;
+//      32-bit entry (code << 16 | len) per (byte value, lane) at 0x20000 + value * 256 + lane * 4, so the gathers of
+//      a warp can never conflict) and one LDS; four codewords are concatenated into a 64-bit chunk by multiply-adds
+//      with 2^len (one SHF each; FMA pipe), the chunk length is the sum of the entries' low halves;
 //   2. warp-shuffle scan of the thread bit counts, the eight warp totals cross the first named barrier; the tile's
 //      bit count is published at once as (AGGREGATE | bits);
 //   3. staging: every chunk is OR-ed into one of the group's THREE zeroed staging buffers at its tile-relative bit
@@ -66,9 +66,11 @@ constexpr u32 kEncLutAddr = 0x20000u;
 constexpr u32 kEncLutBytes = 256u * 256u;
 struct EncGroupCtl {
   u32 wtot[kEncGroupWarps];  // warp totals of the tile being counted
-  u64 tile_start;
+  // the tiles staged in the group's buffers (group-uniform state lives here, not in every thread's registers)
+  u64 s_tile[kEncBufs];
+  u64 s_G[kEncBufs];
+  u32 s_bits[kEncBufs];
   u32 next_tile;
-  u32 pad[5];
 };
 struct EncLowSmem {  // at the start of dynamic shared memory
   EncGroupCtl ctl[kEncGroups];
@@ -97,18 +99,19 @@ __device__ __forceinline__ void group_barrier(unsigned group) {
 }
 
 // ---- table gather --------------------------------------------------------------------------------------------------
+// entry of (byte value v, lane l): one 32-bit word (code << 16 | len [| long flag]) at kEncLutAddr + v * 256 + l * 4
 #ifdef GH_EMUL
 typedef const unsigned char* enc_lut_t;  // the table's base plus this lane's column
-__device__ __forceinline__ uint2 enc_lut_entry(enc_lut_t lut_lane, u32 word, int k) {
-  return *reinterpret_cast<const uint2*>(lut_lane + (((word >> (8 * k)) & 0xffu) << 8));
+__device__ __forceinline__ u32 enc_lut_entry(enc_lut_t lut_lane, u32 word, int k) {
+  return *reinterpret_cast<const u32*>(lut_lane + (((word >> (8 * k)) & 0xffu) << 8));
 }
 #else
-typedef u32 enc_lut_t;  // kEncLutAddr | lane * 8
-__device__ __forceinline__ uint2 enc_lut_entry(enc_lut_t lut_lane, u32 word, int k) {
-  // address = 0x00 0x02 <byte k of word> <lane * 8>: bytes 3 and 2 and 0 from lut_lane, byte 1 from the input word
-  const u32 addr = __byte_perm(word, lut_lane, 0x7604u | (u32(k) << 4));  // bytes 3, 2 (0x0002) and 0 of lut_lane
-  uint2 v;
-  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+typedef u32 enc_lut_t;  // kEncLutAddr | lane * 4
+__device__ __forceinline__ u32 enc_lut_entry(enc_lut_t lut_lane, u32 word, int k) {
+  // address = 0x00 0x02 <byte k of word> <lane * 4>: bytes 3, 2 and 0 from lut_lane, byte 1 from the input word
+  const u32 addr = __byte_perm(word, lut_lane, 0x7604u | (u32(k) << 4));
+  u32 v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 #endif
@@ -222,9 +225,9 @@ __device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 t
 
 // copy-out of one staged tile: `nthr` threads (this one is number `t`) store the words of the tile that starts at
 // global bit G, reading the bit string staged at `stage`
-__device__ __forceinline__ void enc_copy_out(enc_stage_t stage, u32 tile_bits, u64 tile, u64 G, bool last_tile, int append_eof,
+__device__ __noinline__ void enc_copy_out(enc_stage_t stage, u32 tile_bits, u64 tile, u64 G, bool last_tile, int append_eof,
                                              u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out,
-                                             const EncWorkspace& ws, u32 t, u32 nthr) {
+                                             u32* __restrict__ head, u32 t, u32 nthr) {
   const u32 phase = u32(G) & 31u;
   const u64 end_bit = G + tile_bits;
   const u64 word0 = G >> 5;
@@ -233,8 +236,34 @@ __device__ __forceinline__ void enc_copy_out(enc_stage_t stage, u32 tile_bits, u
   u32* const dst = out_words + word0;
   const u64 room = out_word_cap > word0 ? out_word_cap - word0 : 0;
   const u32 lim = u64(nwords - 1u) < room ? nwords - 1u : u32(room);  // interior words: 1 .. nwords - 2
+#ifdef GH_EMUL
   for (u32 i = t + 1u; i < lim; i += nthr)
     dst[i] = be32(__funnelshift_r(enc_stage_ld(stage, i, 0), enc_stage_ld(stage, i, -1), phase));
+#else
+  {
+    // two words per thread and step (independent loads in flight), pointers advanced instead of re-derived
+    u32 sa = stage + (t + 1u) * 4u;
+    u32* gp = dst + (t + 1u);
+    u32 i = t + 1u;
+    for (; i + nthr < lim; i += 2u * nthr) {
+      u32 a0, a1, b0, b1;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(sa));
+      asm("ld.shared.u32 %0, [%1+-4];" : "=r"(a1) : "r"(sa));
+      asm("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(sa + nthr * 4u));
+      asm("ld.shared.u32 %0, [%1+-4];" : "=r"(b1) : "r"(sa + nthr * 4u));
+      gp[0] = be32(__funnelshift_r(a0, a1, phase));
+      gp[nthr] = be32(__funnelshift_r(b0, b1, phase));
+      sa += 2u * nthr * 4u;
+      gp += 2u * nthr;
+    }
+    if (i < lim) {
+      u32 a0, a1;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(sa));
+      asm("ld.shared.u32 %0, [%1+-4];" : "=r"(a1) : "r"(sa));
+      gp[0] = be32(__funnelshift_r(a0, a1, phase));
+    }
+  }
+#endif
   // first and last word of the tile
   if (t < 2u && (t == 0 || nwords > 1u)) {
     const u32 i = t == 0 ? 0u : nwords - 1u;
@@ -243,7 +272,7 @@ __device__ __forceinline__ void enc_copy_out(enc_stage_t stage, u32 tile_bits, u
       const u32 pad = u32((8 - (end_bit & 7)) & 7);  // flush_bits(): 1s up to the byte boundary
       if (pad) v |= ((1u << pad) - 1u) << (32u - (u32(end_bit & 31) + pad));
     }
-    if (i == 0 && tile > 0 && phase != 0) ws.head[tile] = v;  // shared with the previous tile: stitched later
+    if (i == 0 && tile > 0 && phase != 0) head[tile] = v;  // shared with the previous tile: stitched later
     else if (u64(i) < room) dst[i] = be32(v);
   }
 }
@@ -252,12 +281,6 @@ __device__ __forceinline__ void enc_clear(u32* buf, u32 tile_bits, u32 t) {
   uint4* const z = reinterpret_cast<uint4*>(buf);
   for (u32 i = t; i < (tile_bits >> 7) + 1u; i += kEncGroupThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
 }
-
-struct EncPending {  // a staged tile of the group (group-uniform values)
-  bool valid;
-  u32 bits, buf;
-  u64 tile, G;
-};
 
 __global__ void __launch_bounds__(kEncThreads, 1)
 encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
@@ -294,11 +317,10 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   for (unsigned i = threadIdx.x; i < 256u * 32u; i += kEncThreads) {
     const unsigned sym = i >> 5, col = i & 31;
     const u32 len = table.length[sym];
-    uint2 e;
-    if (len == 0) e = make_uint2(0u, 1u);                                     // byte value that does not occur
-    else if (len <= 16) e = make_uint2((table.codeword[sym] << 16) | len, 1u << len);
-    else e = make_uint2(kEncLongFlag, 1u);                                    // handled by the slow path
-    *reinterpret_cast<uint2*>(lut_ptr + sym * 256u + col * 8u) = e;
+    u32 e = 0;                                                  // byte value that does not occur
+    if (len != 0 && len <= 16) e = (table.codeword[sym] << 16) | len;
+    else if (len > 16) e = kEncLongFlag;                        // handled by the slow path
+    *reinterpret_cast<u32*>(lut_ptr + sym * 256u + col * 4u) = e;
   }
   for (unsigned i = threadIdx.x; i < unsigned(GH_NSYM); i += kEncThreads)
     low.long_table[i] = make_uint2(table.codeword[i], u32(table.length[i]));
@@ -306,9 +328,9 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   if (tg == 0) ctl.next_tile = atomicAdd(ws.ticket, 1u);
   __syncthreads();
 #ifdef GH_EMUL
-  const enc_lut_t lut_lane = lut_ptr + lane * 8u;
+  const enc_lut_t lut_lane = lut_ptr + lane * 4u;
 #else
-  const enc_lut_t lut_lane = kEncLutAddr | (lane * 8u);
+  const enc_lut_t lut_lane = kEncLutAddr | (lane * 4u);
 #endif
   const uint2* const long_table = low.long_table;
   const u64 ntiles = enc_num_tiles(n);
@@ -318,35 +340,36 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   const u32 off = tg * kEncBytesPerThread;           // this thread's slice inside a tile
   const u32 row = (tg & ~31u) * kEncBytesPerThread;  // its warp's row
 
-  u32 cur = 0;     // buffer the next tile is staged into
-  EncPending A;    // staged, start bit not resolved yet (the previous tile)
-  EncPending B;    // staged and resolved, awaits its copy-out (the tile before that)
-  A.valid = B.valid = false;
-  A.bits = B.bits = A.buf = B.buf = 0;
-  A.tile = B.tile = A.G = B.G = 0;
+  u32 cur = 0;          // buffer the next tile is staged into
+  bool a_valid = false;  // buffer cur - 1 holds a staged tile whose start bit is not resolved yet (the previous tile)
+  bool b_valid = false;  // buffer cur - 2 holds a staged and resolved tile that awaits its copy-out
+  auto prev_buf = [](u32 b) -> u32 { return b == 0 ? u32(kEncBufs - 1) : b - 1u; };
 
-  auto copy_out = [&](const EncPending& p, u32 t, u32 nthr) {
-    enc_copy_out(enc_stage_handle(buf_ptr0 + p.buf * kEncBufWords), p.bits, p.tile, p.G, p.tile + 1 == ntiles, append_eof,
-                 out_words, out_word_cap, end_bit_out, ws, t, nthr);
+  auto copy_out = [&](u32 buf, u32 t, u32 nthr) {
+    const u64 ptile = ctl.s_tile[buf];
+    enc_copy_out(enc_stage_handle(buf_ptr0 + buf * kEncBufWords), ctl.s_bits[buf], ptile, ctl.s_G[buf], ptile + 1 == ntiles,
+                 append_eof, out_words, out_word_cap, end_bit_out, ws.head, t, nthr);
+  };
+  auto resolve = [&](u32 buf) {  // warp 0: look-back of the tile staged in `buf`
+    const u64 g = tile_start_lookback(ws, ctl.s_tile[buf], ctl.s_bits[buf], start_bit, lane);
+    if (lane == 0) ctl.s_G[buf] = g;
   };
   // completes the pending tiles with the whole group (big-tile path and the end of the loop)
   auto drain = [&]() {
-    group_barrier(group);  // every thread has taken B.G and the next tile's number from ctl (they are rewritten below)
-    if (B.valid) copy_out(B, tg, kEncGroupThreads);
-    if (A.valid && wg == 0) {
-      const u64 g = tile_start_lookback(ws, A.tile, A.bits, start_bit, lane);
-      if (lane == 0) ctl.tile_start = g;
-    }
+    const u32 ab = prev_buf(cur), bb = prev_buf(ab);
     group_barrier(group);
-    if (B.valid) enc_clear(buf_ptr0 + B.buf * kEncBufWords, B.bits, tg);
-    if (A.valid) {
-      A.G = ctl.tile_start;
-      copy_out(A, tg, kEncGroupThreads);
+    if (b_valid) copy_out(bb, tg, kEncGroupThreads);
+    if (a_valid && wg == 0) resolve(ab);
+    group_barrier(group);
+    if (b_valid) enc_clear(buf_ptr0 + bb * kEncBufWords, ctl.s_bits[bb], tg);
+    if (a_valid) {
+      copy_out(ab, tg, kEncGroupThreads);
       group_barrier(group);
-      enc_clear(buf_ptr0 + A.buf * kEncBufWords, A.bits, tg);
+      enc_clear(buf_ptr0 + ab * kEncBufWords, ctl.s_bits[ab], tg);
     }
-    A.valid = B.valid = false;
+    a_valid = b_valid = false;
   };
+  const u32 total_groups = gridDim.x * u32(kEncGroups);
 
   u64 tile = ctl.next_tile;
   while (tile < ntiles) {
@@ -368,19 +391,22 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
 #pragma unroll
     for (int c = 0; c < kEncChunks; ++c) {
       const u32 word = vec.w[c];
-      const uint2 e0 = enc_lut_entry(lut_lane, word, 0);
-      const uint2 e1 = enc_lut_entry(lut_lane, word, 1);
-      const uint2 e2 = enc_lut_entry(lut_lane, word, 2);
-      const uint2 e3 = enc_lut_entry(lut_lane, word, 3);
+      const u32 e0 = enc_lut_entry(lut_lane, word, 0);
+      const u32 e1 = enc_lut_entry(lut_lane, word, 1);
+      const u32 e2 = enc_lut_entry(lut_lane, word, 2);
+      const u32 e3 = enc_lut_entry(lut_lane, word, 3);
+      // 2^len of the three codewords that get shifted over: SHF takes its distance modulo 32 and len <= 16 sits in
+      // the entry's low bits, so the entry itself is the shift operand
+      const u32 p1 = __funnelshift_l(0u, 1u, e1), p2 = __funnelshift_l(0u, 1u, e2), p3 = __funnelshift_l(0u, 1u, e3);
       // acc = ((c0 * 2^l1 + c1) * 2^l2 * 2^l3) + (c2 * 2^l3 + c3): products on the FMA pipe; the additions cannot
       // carry because the products' low bits are zero
-      const u32 a01 = __umulhi(e0.x, 1u << 16) * e1.y + __umulhi(e1.x, 1u << 16);  // <= 32 bits
-      const u32 a23 = __umulhi(e2.x, 1u << 16) * e3.y + __umulhi(e3.x, 1u << 16);  // <= 32 bits
-      const u64 t = u64(a01) * e2.y;                                               // <= 48 bits
-      const u64 acc = t * e3.y + a23;
-      c_lo[c] = u32(acc);
-      c_hi[c] = u32(acc >> 32);
-      const u32 l = (e0.x + e1.x + e2.x + e3.x) & 0xffffu;  // lengths (and long-codeword flags) add up in the low half
+      const u32 a01 = __umulhi(e0, 1u << 16) * p1 + __umulhi(e1, 1u << 16);  // <= 32 bits
+      const u32 a23 = __umulhi(e2, 1u << 16) * p3 + __umulhi(e3, 1u << 16);  // <= 32 bits
+      const u64 t = u64(a01) * p2;                                            // <= 48 bits
+      const u64 u = u64(u32(t)) * p3;
+      c_lo[c] = u32(u) + a23;
+      c_hi[c] = u32(t >> 32) * p3 + u32(u >> 32);
+      const u32 l = (e0 + e1 + e2 + e3) & 0xffffu;  // lengths (and long-codeword flags) add up in the low half
       flags |= l;
       bits += l;
       c_end[c] = bits;  // end of this chunk relative to the thread's first bit
@@ -418,15 +444,21 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       tile_bits = __shfl_sync(0xffffffffu, v, kEncGroupWarps - 1);
       wprefix = __shfl_sync(0xffffffffu, v, int(wg)) - __shfl_sync(0xffffffffu, incl, 31);
     }
-    // the tile's count is known to everybody a whole tile period before its own look-back runs
-    if (tg == 0) st_volatile_u64(ws.tile_state + tile, tile > 0 ? (kFlagAggregate | u64(tile_bits)) : (kFlagPrefix | (start_bit + tile_bits)));
-    const u32 pos = wprefix + incl - bits;
     const bool big = tile_bits > kEncBufBits;  // group-uniform
+    // the tile's count is known to everybody a whole tile period before its own look-back runs
+    if (tg == 0) {
+      st_volatile_u64(ws.tile_state + tile, tile > 0 ? (kFlagAggregate | u64(tile_bits)) : (kFlagPrefix | (start_bit + tile_bits)));
+    }
+    const u32 pos = wprefix + incl - bits;
     if (big) {
       // rare: the tile needs all three buffers. The pending tiles leave first, then this one, at once.
       drain();
       group_barrier(group);
       cur = 0;
+    }
+    if (tg == 0) {  // read by the group after barrier (b)
+      ctl.s_tile[cur] = tile;
+      ctl.s_bits[cur] = tile_bits;
     }
     // ---- 3. staging at tile-relative positions -------------------------------------------------------------------
     const enc_stage_t stage = enc_stage_handle(buf_ptr0 + cur * kEncBufWords);
@@ -440,27 +472,28 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       if (owns_end && eof_len) stage_chunk(stage, p2 + eof_len, eof_code, 0u);
     }
     // ---- 4. + 5. warp 0: the previous tile's start bit, the next tile's number; the others: copy-out of tile k-2 -----
-    if (wg == 0) {
-      u64 g = 0;
-      if (A.valid) g = tile_start_lookback(ws, A.tile, A.bits, start_bit, lane);
-      if (lane == 0) {
-        ctl.tile_start = g;
-        ctl.next_tile = atomicAdd(ws.ticket, 1u);
+    {
+      const u32 ab = prev_buf(cur), bb = prev_buf(ab);
+      if (wg == 0) {
+        if (a_valid) resolve(ab);
+        if (lane == 0) {
+          const u32 nt = atomicAdd(ws.ticket, 1u);
+          ctl.next_tile = nt;
+          // the tile somebody will draw about one tile period from now: start its way from DRAM to L2
+          const u64 ahead = u64(nt) + total_groups;
+          if (ahead + 1 < ntiles) prefetch_l2_bulk(in + ahead * kEncTileBytes, kEncTileBytes);
+        }
+      } else if (b_valid) {
+        copy_out(bb, tg - 32u, kEncGroupThreads - 32u);
       }
-    } else if (B.valid) {
-      copy_out(B, tg - 32u, kEncGroupThreads - 32u);
+      group_barrier(group);  // (b) tile k staged, G of tile k-1 and the next tile's number known, tile k-2 read
+      if (b_valid) enc_clear(buf_ptr0 + bb * kEncBufWords, ctl.s_bits[bb], tg);
     }
-    group_barrier(group);  // (b) tile k staged, G of tile k-1 and the next tile's number known, tile k-2 read
-    if (B.valid) enc_clear(buf_ptr0 + B.buf * kEncBufWords, B.bits, tg);
-    B = A;
-    B.G = ctl.tile_start;
-    A.valid = true;
-    A.bits = tile_bits;
-    A.buf = cur;
-    A.tile = tile;
+    b_valid = a_valid;
+    a_valid = true;
     cur = cur == u32(kEncBufs - 1) ? 0u : cur + 1u;
     if (big) {
-      drain();  // B is invalid here; A (this tile, from buffer 0 across all three) is resolved and copied out
+      drain();  // b is invalid here; a (this tile, from buffer 0 across all three) is resolved and copied out
       cur = 0;
     }
     tile = ctl.next_tile;

@@ -186,11 +186,21 @@ __device__ __noinline__ u32 stage_slow(enc_stage_t stage, u32 pos, const uint2* 
 // Decoupled look-back by one whole warp. The tile's own count was published before (AGGREGATE; tile 0: PREFIX);
 // this adds up the predecessors' counts back to the nearest tile that already knows its start, publishes this
 // tile's end bit and returns its start bit (all 32 lanes must call it together).
-__device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 tile, u32 tile_bits, u64 start_bit, unsigned lane) {
+// `early` = the state of tile - 1 - lane, loaded by the caller some time before (0 = not loaded): it serves as a first
+// round over 32 predecessors whose latency was hidden behind the caller's other work.
+__device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 tile, u32 tile_bits, u64 start_bit, unsigned lane,
+                                                   u64 early) {
   if (tile == 0) return start_bit;  // tile 0 published its PREFIX when it was counted
   u64 exclusive = 0;
   long long look = (long long)tile - 1;
   bool done = false;
+  if (__all_sync(0xffffffffu, (early & kFlagMask) != 0)) {  // every one of the 32 is published
+    const unsigned has_prefix = __ballot_sync(0xffffffffu, (early & kFlagMask) == kFlagPrefix);
+    const unsigned first = unsigned(__ffs(int(has_prefix))) - 1u;
+    exclusive = warp_sum64((has_prefix == 0 || lane <= first) ? (early & ~kFlagMask) : 0ull);
+    done = has_prefix != 0;
+    look -= 32;
+  }
   while (!done) {
     // One round trip covers 32 x kEncLookDepth predecessors: lane l owns the consecutive tiles
     // look - l * kEncLookDepth - r (r = 0 nearest), loads all of them at once, folds them locally (sum of
@@ -225,7 +235,7 @@ __device__ __forceinline__ u64 tile_start_lookback(const EncWorkspace& ws, u64 t
 
 // copy-out of one staged tile: `nthr` threads (this one is number `t`) store the words of the tile that starts at
 // global bit G, reading the bit string staged at `stage`
-__device__ __noinline__ void enc_copy_out(enc_stage_t stage, u32 tile_bits, u64 tile, u64 G, bool last_tile, int append_eof,
+__device__ __forceinline__ void enc_copy_out(enc_stage_t stage, u32 tile_bits, u64 tile, u64 G, bool last_tile, int append_eof,
                                              u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out,
                                              u32* __restrict__ head, u32 t, u32 nthr) {
   const u32 phase = u32(G) & 31u;
@@ -340,165 +350,157 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
   const u32 off = tg * kEncBytesPerThread;           // this thread's slice inside a tile
   const u32 row = (tg & ~31u) * kEncBytesPerThread;  // its warp's row
 
-  u32 cur = 0;          // buffer the next tile is staged into
-  bool a_valid = false;  // buffer cur - 1 holds a staged tile whose start bit is not resolved yet (the previous tile)
-  bool b_valid = false;  // buffer cur - 2 holds a staged and resolved tile that awaits its copy-out
-  auto prev_buf = [](u32 b) -> u32 { return b == 0 ? u32(kEncBufs - 1) : b - 1u; };
-
-  auto copy_out = [&](u32 buf, u32 t, u32 nthr) {
-    const u64 ptile = ctl.s_tile[buf];
-    enc_copy_out(enc_stage_handle(buf_ptr0 + buf * kEncBufWords), ctl.s_bits[buf], ptile, ctl.s_G[buf], ptile + 1 == ntiles,
-                 append_eof, out_words, out_word_cap, end_bit_out, ws.head, t, nthr);
-  };
-  auto resolve = [&](u32 buf) {  // warp 0: look-back of the tile staged in `buf`
-    const u64 g = tile_start_lookback(ws, ctl.s_tile[buf], ctl.s_bits[buf], start_bit, lane);
-    if (lane == 0) ctl.s_G[buf] = g;
-  };
-  // completes the pending tiles with the whole group (big-tile path and the end of the loop)
-  auto drain = [&]() {
-    const u32 ab = prev_buf(cur), bb = prev_buf(ab);
-    group_barrier(group);
-    if (b_valid) copy_out(bb, tg, kEncGroupThreads);
-    if (a_valid && wg == 0) resolve(ab);
-    group_barrier(group);
-    if (b_valid) enc_clear(buf_ptr0 + bb * kEncBufWords, ctl.s_bits[bb], tg);
-    if (a_valid) {
-      copy_out(ab, tg, kEncGroupThreads);
-      group_barrier(group);
-      enc_clear(buf_ptr0 + ab * kEncBufWords, ctl.s_bits[ab], tg);
-    }
-    a_valid = b_valid = false;
-  };
+  // The group's pipeline: tile k is staged into buffer `cur` while tile k-1 (`a`, staged, start bit not resolved yet)
+  // is resolved by warp 0 and tile k-2 (`b`, resolved) is copied out by warps 1-7. Iterations that cannot stage a tile
+  // (no tile left; a big tile waiting for the pipeline to empty, or occupying all buffers) only advance the pipeline.
+  u32 cur = 0, a_buf = 0, b_buf = 0;
+  bool a_valid = false, b_valid = false;
+  bool big_hold = false;  // a big tile is in the pipeline: nothing else may be staged
   const u32 total_groups = gridDim.x * u32(kEncGroups);
 
   u64 tile = ctl.next_tile;
-  while (tile < ntiles) {
-    const u64 tile_base = tile * kEncTileBytes;
-    const uint8_t* const tin = in + tile_base;
-    const u64 left = n - tile_base;
-    const u32 rem = left < u64(kEncTileBytes) ? u32(left) : u32(kEncTileBytes);  // short only for the last tile
-    const bool last_tile = (tile + 1 == ntiles);
-    EncVec vec;
-    if (off + kEncBytesPerThread <= rem) {
-      vec = enc_load_vec(tin + off, aligned32);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) vec.w[k] = 0;
-    }
-    // ---- 1. gather + concatenate -----------------------------------------------------------------------------
+  while (tile < ntiles || a_valid || b_valid) {
+    bool staged = false, big = false;
     u32 c_lo[kEncChunks], c_hi[kEncChunks], c_end[kEncChunks];
-    u32 bits = 0, flags = 0;
-#pragma unroll
-    for (int c = 0; c < kEncChunks; ++c) {
-      const u32 word = vec.w[c];
-      const u32 e0 = enc_lut_entry(lut_lane, word, 0);
-      const u32 e1 = enc_lut_entry(lut_lane, word, 1);
-      const u32 e2 = enc_lut_entry(lut_lane, word, 2);
-      const u32 e3 = enc_lut_entry(lut_lane, word, 3);
-      // 2^len of the three codewords that get shifted over: SHF takes its distance modulo 32 and len <= 16 sits in
-      // the entry's low bits, so the entry itself is the shift operand
-      const u32 p1 = __funnelshift_l(0u, 1u, e1), p2 = __funnelshift_l(0u, 1u, e2), p3 = __funnelshift_l(0u, 1u, e3);
-      // acc = ((c0 * 2^l1 + c1) * 2^l2 * 2^l3) + (c2 * 2^l3 + c3): products on the FMA pipe; the additions cannot
-      // carry because the products' low bits are zero
-      const u32 a01 = __umulhi(e0, 1u << 16) * p1 + __umulhi(e1, 1u << 16);  // <= 32 bits
-      const u32 a23 = __umulhi(e2, 1u << 16) * p3 + __umulhi(e3, 1u << 16);  // <= 32 bits
-      const u64 t = u64(a01) * p2;                                            // <= 48 bits
-      const u64 u = u64(u32(t)) * p3;
-      c_lo[c] = u32(u) + a23;
-      c_hi[c] = u32(t >> 32) * p3 + u32(u >> 32);
-      const u32 l = (e0 + e1 + e2 + e3) & 0xffffu;  // lengths (and long-codeword flags) add up in the low half
-      flags |= l;
-      bits += l;
-      c_end[c] = bits;  // end of this chunk relative to the thread's first bit
-    }
-    // rows that need the slow path: a long codeword, the ragged end, or the byte the end mark follows
-    const bool row_live = row < rem;
-    const bool row_end = last_tile && row + kEncRowBytes >= rem;
-    bool slow = false;
+    u32 bits = 0, pos = 0, tile_bits = 0;
+    bool slow = false, row_live = false, owns_end = false;
     int cnt = 0;
-    bool owns_end = false;
-    if (row_live) {
-      slow = row_end || __any_sync(0xffffffffu, (flags & 0xf000u) != 0u);
-      if (slow) {
-        cnt = off >= rem ? 0 : (rem - off < u32(kEncBytesPerThread) ? int(rem - off) : kEncBytesPerThread);
-        bits = count_slow(long_table, tin + off, cnt);
-        owns_end = last_tile && cnt > 0 && off + u32(cnt) == rem;
-        if (owns_end) bits += eof_len;
-      }
-    } else {
-      bits = 0;
-    }
-    // ---- 2. scan ---------------------------------------------------------------------------------------------
-    const u32 incl = warp_inclusive_scan(bits, lane);
-    if (lane == 31) ctl.wtot[wg] = incl;
-    group_barrier(group);  // (a) warp totals; every clear of the previous iteration is done
-    u32 wprefix, tile_bits;
-    {
-      // the eight warp totals, scanned by every warp for itself
-      u32 v = lane < u32(kEncGroupWarps) ? ctl.wtot[lane] : 0u;
+    const uint8_t* tin = in;
+    if (tile < ntiles && !big_hold) {
+      const u64 tile_base = tile * kEncTileBytes;
+      tin = in + tile_base;
+      const u64 left = n - tile_base;
+      const u32 rem = left < u64(kEncTileBytes) ? u32(left) : u32(kEncTileBytes);  // short only for the last tile
+      const bool last_tile = (tile + 1 == ntiles);
+      EncVec vec;
+      if (off + kEncBytesPerThread <= rem) {
+        vec = enc_load_vec(tin + off, aligned32);
+      } else {
 #pragma unroll
-      for (int d = 1; d < kEncGroupWarps; d <<= 1) {
-        const u32 up = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= unsigned(d)) v += up;
+        for (int k = 0; k < 8; ++k) vec.w[k] = 0;
       }
-      tile_bits = __shfl_sync(0xffffffffu, v, kEncGroupWarps - 1);
-      wprefix = __shfl_sync(0xffffffffu, v, int(wg)) - __shfl_sync(0xffffffffu, incl, 31);
-    }
-    const bool big = tile_bits > kEncBufBits;  // group-uniform
-    // the tile's count is known to everybody a whole tile period before its own look-back runs
-    if (tg == 0) {
-      st_volatile_u64(ws.tile_state + tile, tile > 0 ? (kFlagAggregate | u64(tile_bits)) : (kFlagPrefix | (start_bit + tile_bits)));
-    }
-    const u32 pos = wprefix + incl - bits;
-    if (big) {
-      // rare: the tile needs all three buffers. The pending tiles leave first, then this one, at once.
-      drain();
-      group_barrier(group);
-      cur = 0;
-    }
-    if (tg == 0) {  // read by the group after barrier (b)
-      ctl.s_tile[cur] = tile;
-      ctl.s_bits[cur] = tile_bits;
-    }
-    // ---- 3. staging at tile-relative positions -------------------------------------------------------------------
-    const enc_stage_t stage = enc_stage_handle(buf_ptr0 + cur * kEncBufWords);
-    if (!slow) {
+      // ---- 1. gather + concatenate ---------------------------------------------------------------------------
+      u32 flags = 0;
+#pragma unroll
+      for (int c = 0; c < kEncChunks; ++c) {
+        const u32 word = vec.w[c];
+        const u32 e0 = enc_lut_entry(lut_lane, word, 0);
+        const u32 e1 = enc_lut_entry(lut_lane, word, 1);
+        const u32 e2 = enc_lut_entry(lut_lane, word, 2);
+        const u32 e3 = enc_lut_entry(lut_lane, word, 3);
+        // 2^len of the three codewords that get shifted over: SHF takes its distance modulo 32 and len <= 16 sits in
+        // the entry's low bits, so the entry itself is the shift operand
+        const u32 p1 = __funnelshift_l(0u, 1u, e1), p2 = __funnelshift_l(0u, 1u, e2), p3 = __funnelshift_l(0u, 1u, e3);
+        // acc = ((c0 * 2^l1 + c1) * 2^l2 * 2^l3) + (c2 * 2^l3 + c3): products on the FMA pipe; the additions cannot
+        // carry because the products' low bits are zero
+        const u32 a01 = __umulhi(e0, 1u << 16) * p1 + __umulhi(e1, 1u << 16);  // <= 32 bits
+        const u32 a23 = __umulhi(e2, 1u << 16) * p3 + __umulhi(e3, 1u << 16);  // <= 32 bits
+        const u64 t = u64(a01) * p2;                                            // <= 48 bits
+        const u64 u = u64(u32(t)) * p3;
+        c_lo[c] = u32(u) + a23;
+        c_hi[c] = u32(t >> 32) * p3 + u32(u >> 32);
+        const u32 l = (e0 + e1 + e2 + e3) & 0xffffu;  // lengths (and long-codeword flags) add up in the low half
+        flags |= l;
+        bits += l;
+        c_end[c] = bits;  // end of this chunk relative to the thread's first bit
+      }
+      // rows that need the slow path: a long codeword, the ragged end, or the byte the end mark follows
+      row_live = row < rem;
+      const bool row_end = last_tile && row + kEncRowBytes >= rem;
       if (row_live) {
-#pragma unroll
-        for (int c = 0; c < kEncChunks; ++c) stage_chunk(stage, pos + c_end[c], c_lo[c], c_hi[c]);
+        slow = row_end || __any_sync(0xffffffffu, (flags & 0xf000u) != 0u);
+        if (slow) {
+          cnt = off >= rem ? 0 : (rem - off < u32(kEncBytesPerThread) ? int(rem - off) : kEncBytesPerThread);
+          bits = count_slow(long_table, tin + off, cnt);
+          owns_end = last_tile && cnt > 0 && off + u32(cnt) == rem;
+          if (owns_end) bits += eof_len;
+        }
+      } else {
+        bits = 0;
       }
-    } else {
-      const u32 p2 = stage_slow(stage, pos, long_table, tin + off, cnt);
-      if (owns_end && eof_len) stage_chunk(stage, p2 + eof_len, eof_code, 0u);
+      // ---- 2. scan -------------------------------------------------------------------------------------------
+      const u32 incl = warp_inclusive_scan(bits, lane);
+      if (lane == 31) ctl.wtot[wg] = incl;
+      group_barrier(group);  // (a) warp totals; every clear of the previous iteration is done
+      u32 wprefix;
+      {
+        // the eight warp totals, scanned by every warp for itself
+        u32 v = lane < u32(kEncGroupWarps) ? ctl.wtot[lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < kEncGroupWarps; d <<= 1) {
+          const u32 up = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= unsigned(d)) v += up;
+        }
+        tile_bits = __shfl_sync(0xffffffffu, v, kEncGroupWarps - 1);
+        wprefix = __shfl_sync(0xffffffffu, v, int(wg)) - __shfl_sync(0xffffffffu, incl, 31);
+      }
+      pos = wprefix + incl - bits;
+      big = tile_bits > kEncBufBits;  // group-uniform
+      // the tile's count is known to everybody a whole tile period before its own look-back runs
+      if (tg == 0)
+        st_volatile_u64(ws.tile_state + tile, tile > 0 ? (kFlagAggregate | u64(tile_bits)) : (kFlagPrefix | (start_bit + tile_bits)));
+      // a big tile needs all three buffers: it waits (and is gathered again) until the pipeline is empty
+      staged = !(big && (a_valid || b_valid));
+      if (staged && big) cur = 0;
+    }
+    // warp 0 starts the look-back of tile k-1 now; the answer arrives while it stages its share of tile k
+    u64 early = 0;
+    if (wg == 0 && a_valid) {
+      const u64 at = ctl.s_tile[a_buf];
+      if (at > u64(lane)) early = ld_volatile_u64(ws.tile_state + (at - 1 - lane));
+      else early = kFlagPrefix;  // virtual tiles before tile 0 add nothing
+    }
+    if (staged) {
+      if (tg == 0) {  // read by the group after barrier (b)
+        ctl.s_tile[cur] = tile;
+        ctl.s_bits[cur] = tile_bits;
+      }
+      // ---- 3. staging at tile-relative positions ---------------------------------------------------------------
+      const enc_stage_t stage = enc_stage_handle(buf_ptr0 + cur * kEncBufWords);
+      if (!slow) {
+        if (row_live) {
+#pragma unroll
+          for (int c = 0; c < kEncChunks; ++c) stage_chunk(stage, pos + c_end[c], c_lo[c], c_hi[c]);
+        }
+      } else {
+        const u32 p2 = stage_slow(stage, pos, long_table, tin + off, cnt);
+        if (owns_end && eof_len) stage_chunk(stage, p2 + eof_len, eof_code, 0u);
+      }
     }
     // ---- 4. + 5. warp 0: the previous tile's start bit, the next tile's number; the others: copy-out of tile k-2 -----
-    {
-      const u32 ab = prev_buf(cur), bb = prev_buf(ab);
-      if (wg == 0) {
-        if (a_valid) resolve(ab);
-        if (lane == 0) {
-          const u32 nt = atomicAdd(ws.ticket, 1u);
-          ctl.next_tile = nt;
-          // the tile somebody will draw about one tile period from now: start its way from DRAM to L2
-          const u64 ahead = u64(nt) + total_groups;
-          if (ahead + 1 < ntiles) prefetch_l2_bulk(in + ahead * kEncTileBytes, kEncTileBytes);
-        }
-      } else if (b_valid) {
-        copy_out(bb, tg - 32u, kEncGroupThreads - 32u);
+    if (wg == 0) {
+      if (a_valid) {
+        const u64 g = tile_start_lookback(ws, ctl.s_tile[a_buf], ctl.s_bits[a_buf], start_bit, lane, early);
+        if (lane == 0) ctl.s_G[a_buf] = g;
       }
-      group_barrier(group);  // (b) tile k staged, G of tile k-1 and the next tile's number known, tile k-2 read
-      if (b_valid) enc_clear(buf_ptr0 + bb * kEncBufWords, ctl.s_bits[bb], tg);
+      if (staged && lane == 0) {
+        const u32 nt = atomicAdd(ws.ticket, 1u);
+        ctl.next_tile = nt;
+        // the tile somebody will draw about one tile period from now: start its way from DRAM to L2
+        const u64 ahead = u64(nt) + total_groups;
+        if (ahead + 1 < ntiles) prefetch_l2_bulk(in + ahead * kEncTileBytes, kEncTileBytes);
+      }
+    } else if (b_valid) {
+      const u64 ptile = ctl.s_tile[b_buf];
+      enc_copy_out(enc_stage_handle(buf_ptr0 + b_buf * kEncBufWords), ctl.s_bits[b_buf], ptile, ctl.s_G[b_buf], ptile + 1 == ntiles,
+                   append_eof, out_words, out_word_cap, end_bit_out, ws.head, tg - 32u, kEncGroupThreads - 32u);
     }
+    group_barrier(group);  // (b) tile k staged, G of tile k-1 and the next tile's number known, tile k-2 read
+    if (b_valid) enc_clear(buf_ptr0 + b_buf * kEncBufWords, ctl.s_bits[b_buf], tg);
     b_valid = a_valid;
-    a_valid = true;
-    cur = cur == u32(kEncBufs - 1) ? 0u : cur + 1u;
-    if (big) {
-      drain();  // b is invalid here; a (this tile, from buffer 0 across all three) is resolved and copied out
+    b_buf = a_buf;
+    a_valid = staged;
+    if (staged) {
+      a_buf = cur;
+      cur = cur == u32(kEncBufs - 1) ? 0u : cur + 1u;
+      big_hold = big;
+      tile = ctl.next_tile;
+    }
+    if (big_hold && !a_valid && !b_valid) {  // the big tile has left: all three buffers are clean again
+      big_hold = false;
       cur = 0;
     }
-    tile = ctl.next_tile;
   }
-  drain();
 }
 
 // Second kernel: OR each tile's deferred head bits into the word its predecessor stored.

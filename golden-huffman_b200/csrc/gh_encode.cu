@@ -444,11 +444,16 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
       if (staged && big) cur = 0;
     }
     // warp 0 starts the look-back of tile k-1 now; the answer arrives while it stages its share of tile k
+    // (and draws the group's next tile: the atomic's round trip is hidden the same way)
     u64 early = 0;
-    if (wg == 0 && a_valid) {
-      const u64 at = ctl.s_tile[a_buf];
-      if (at > u64(lane)) early = ld_volatile_u64(ws.tile_state + (at - 1 - lane));
-      else early = kFlagPrefix;  // virtual tiles before tile 0 add nothing
+    u32 next_ticket = 0;
+    if (wg == 0) {
+      if (a_valid) {
+        const u64 at = ctl.s_tile[a_buf];
+        if (at > u64(lane)) early = ld_volatile_u64(ws.tile_state + (at - 1 - lane));
+        else early = kFlagPrefix;  // virtual tiles before tile 0 add nothing
+      }
+      if (staged && lane == 0) next_ticket = atomicAdd(ws.ticket, 1u);
     }
     if (staged) {
       if (tg == 0) {  // read by the group after barrier (b)
@@ -474,7 +479,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
         if (lane == 0) ctl.s_G[a_buf] = g;
       }
       if (staged && lane == 0) {
-        const u32 nt = atomicAdd(ws.ticket, 1u);
+        const u32 nt = next_ticket;
         ctl.next_tile = nt;
         // the tile somebody will draw about one tile period from now: start its way from DRAM to L2
         const u64 ahead = u64(nt) + total_groups;

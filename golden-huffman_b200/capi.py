@@ -53,6 +53,7 @@ SIGNATURES = {
     "gh_profile_enable": (None, [_INT]),
     "gh_profile_fetch": (_SZ, [C.c_char_p, _SZ]),
     "gh_debug_select_writer": (None, [_INT]),
+    "gh_debug_disable_phase_walk": (None, [_INT]),
     "gh_ctx_set_stream": (_INT, [_VP, _VP]),
     "gh_build_code": (_INT, [_VP, _CODEP]),
     "gh_header_bytes": (_SZ, [_CODEP]),

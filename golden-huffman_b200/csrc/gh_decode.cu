@@ -32,8 +32,6 @@
 //
 // Algorithmic traffic: C bytes read + N bytes written; this implementation reads the payload twice
 // (speculate + write), which the roofline accounting in bench.py does NOT credit.
-#include <stdlib.h>
-
 #include "gh_common.cuh"
 
 namespace gh {
@@ -1021,9 +1019,7 @@ __device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32&
       " @pw mad.lo.u32 %3, %4, %10, 0;\n"
       " @pw mov.u32 %4, %7;\n"
       " mov.b64 a, {%5, %6};\n"
-#ifndef GH_PROBE_W_NOSTORE  // tuning probe (wrong output): everything but the 128-bit store
       " @pg st.global.v4.u32 [a], {%0, %1, %2, %3};\n"
-#endif
       " @pg add.cc.u32 %5, %5, 16;\n"
       " @pg addc.u32 %6, %6, 0;\n"
       "}\n"
@@ -1210,6 +1206,10 @@ dec_sub_offsets_kernel(DecGeometry g, DecWorkspace ws) {
   if (i < g.n_sub) ws.out_off[i] = ws.tile_base[blockIdx.x] + warp_base + (incl - count);
 }
 
+#ifndef GH_EXPERIMENTS
+constexpr u32 kFineSubBytes = 2048;  // layout only (the fine pipeline itself is an experiment build)
+#endif
+#ifdef GH_EXPERIMENTS  // not part of the product build: measured slower than the coarse pipeline (profiles/README.md, r1i)
 // ---- fine-grained pipeline: one warp per 2 KiB segment, 64-byte pieces, shared-memory staging -------------------
 // For codes that re-synchronise within a few codewords (anything but near-fixed-length codes) the subsequence is
 // fixed at 2 KiB and handled by a warp:
@@ -1441,39 +1441,32 @@ dec_fine_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, Dec
   }
 }
 
+#endif  // GH_EXPERIMENTS
+
 // ---- host orchestration -------------------------------------------------------------------------------
 // Pipeline choice: 0 = automatic (currently always the coarse one), 1 = always coarse (one thread per
 // subsequence), 2 = always fine (one warp per 2 KiB segment). gh_debug_select_writer / GH_DECODE_PIPELINE
 // ("coarse" / "fine") override the automatic choice for A/B runs; the output is identical either way.
-static int g_pipeline = -1;
-static int pipeline_choice() {
-  if (g_pipeline < 0) {
-    const char* e = getenv("GH_DECODE_PIPELINE");
-    g_pipeline = (e && e[0] == 'c') ? 1 : (e && e[0] == 'f') ? 2 : 0;
-  }
-  return g_pipeline;
-}
+static int g_pipeline = 0;
+static int pipeline_choice() { return g_pipeline; }
+static bool g_no_phase_walk = false;  // gh_debug_disable_phase_walk: tests force the re-walk rounds on 8/9-bit codes
 
-static int set_write_attrs() {  // SmemWrite exceeds the 48 KB a kernel gets without opting in
-  static bool done = false;
-  if (!done) {
-    GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(SmemWrite))));
-    done = true;
-  }
+// Kernels that need more than the 48 KB of dynamic shared memory a kernel gets without opting in. The attribute is
+// per device, so it is set on every call (it costs nothing) rather than once per process.
+static int set_write_attrs() {
+  GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(SmemWrite))));
   return GH_OK;
 }
 
-static int set_fine_attrs() {  // opt-in to > 48 KB of dynamic shared memory for the kernels that need it
-  static bool done = false;
-  if (!done) {
-    GH_CUDA_TRY(cudaFuncSetAttribute(dec_fine_speculate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     int(sizeof(SmemFineSpec))));
-    GH_CUDA_TRY(cudaFuncSetAttribute(dec_fine_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     int(sizeof(SmemFineWrite))));
-    done = true;
-  }
+#ifdef GH_EXPERIMENTS
+static int set_fine_attrs() {
+  GH_CUDA_TRY(cudaFuncSetAttribute(dec_fine_speculate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   int(sizeof(SmemFineSpec))));
+  GH_CUDA_TRY(cudaFuncSetAttribute(dec_fine_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   int(sizeof(SmemFineWrite))));
   return GH_OK;
 }
+#endif
 
 struct DecLayout {
   size_t off_tables, off_lut1, off_lutC, off_lutW, off_lutP, off_ctl, off_sub, off_neof, off_eofpos, off_out_off, off_pieces, off_work0, off_work1, off_ph_fn, off_ph_cnt, off_ph_first, off_ph_neof, off_ph_tile_fn, off_ph_tile_entry, off_tile_sum, off_tile_base, total;
@@ -1546,22 +1539,36 @@ static u32 choose_sub_bytes(u64 slice_bytes) {
   return u32(s);
 }
 
-static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream, bool fine) {
+static int dec_finish_launch(const DecGeometry& g, const DecWorkspace& ws, cudaStream_t stream, bool fine) {
   const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
   GH_LAUNCH(dec_tile_sum_kernel, tiles, kDecThreads, 0, stream, g, ws);
   GH_LAUNCH(dec_locate_eof_kernel, 1, kDecThreads, 0, stream, g, ws);
   GH_LAUNCH(dec_offsets_kernel, 1, kScanThreads, 0, stream, g, ws);
   if (fine) GH_LAUNCH(dec_sub_offsets_kernel, tiles, kDecThreads, 0, stream, g, ws);  // only the fine writer reads out_off
-  int rc = check_launch();
-  if (rc != GH_OK) return rc;
+  return check_launch();
+}
+
+static int dec_read_ctl(const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream) {
   GH_CUDA_TRY(cudaMemcpyAsync(h_ctl, ws.ctl, sizeof(DecControl), cudaMemcpyDeviceToHost, stream));
   GH_CUDA_TRY(cudaStreamSynchronize(stream));
   return GH_OK;
 }
 
+static int dec_finish(const DecGeometry& g, const DecWorkspace& ws, DecControl* h_ctl, cudaStream_t stream, bool fine) {
+  int rc = dec_finish_launch(g, ws, stream, fine);
+  if (rc != GH_OK) return rc;
+  return dec_read_ctl(ws, h_ctl, stream);
+}
+
+// `deferred` (whole-image decode only): when non-null, the common case enqueues one synchronisation round and the
+// offset kernels WITHOUT reading the control block back -- the caller enqueues the writer behind them and reads the
+// control block once, after everything; *deferred tells it that `result` is still to be filled from that read. If the
+// round turns out not to have been clean (an exit moved: rare, the paths of a self-synchronising code meet within a
+// few codewords), the caller repeats the decode with deferred == nullptr.
 static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 readable, const gh_code* code, u32 entry_bit,
                             int first_call, gh_shard_sync* result, void* d_ws, size_t ws_bytes, cudaStream_t stream,
-                            DecGeometry* geom_out, bool* fine_out = nullptr) {
+                            DecGeometry* geom_out, bool* fine_out = nullptr, bool* deferred = nullptr) {
+  if (deferred) *deferred = false;
   if (!d_payload || !code || !d_ws) return GH_ERR_ARG;
   if (slice_bytes == 0) return GH_ERR_NO_EOF;
   if ((reinterpret_cast<uintptr_t>(d_payload) & 15) || (reinterpret_cast<uintptr_t>(d_ws) & 255)) return GH_ERR_ARG;
@@ -1604,7 +1611,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   bool phase = false;
   u32 eof_v = 2;  // value of the end mark's ninth bit (2: the end mark is not a 9-bit codeword)
   if (code->min_len == 8 && code->max_len == 9 && code->first_code[8] == 1 && code->first_code[9] == 0 &&
-      slice_bytes >= 4 * kPhaseMinSub && pipeline_choice() != 2 && !getenv("GH_NO_PHASE_WALK")) {
+      slice_bytes >= 4 * kPhaseMinSub && pipeline_choice() != 2 && !g_no_phase_walk) {
     phase = first_call ? true : h_ctl.phase != 0;
     for (u32 v = 0; v < 2; ++v) {
       const u32 idx = code->start_pos[9] + v;
@@ -1634,6 +1641,12 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     GH_LAUNCH(dec_phase_finish_kernel, blocks, kDecThreads, 0, stream, g, ws, (const u32*)ws.work[0]);
     int rc = check_launch();
     if (rc != GH_OK) return rc;
+    if (geom_out) *geom_out = g;
+    if (fine_out) *fine_out = false;
+    if (deferred) {  // the phase walk needs no rounds: nothing to confirm, only the totals to read later
+      *deferred = true;
+      return dec_finish_launch(g, ws, stream, false);
+    }
     rc = dec_finish(g, ws, &h_ctl, stream, false);
     if (rc != GH_OK) return rc;
     if (result) {
@@ -1643,8 +1656,6 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
       result->rounds = 1;
       result->sub_bytes = g.sub_bytes;
     }
-    if (geom_out) *geom_out = g;
-    if (fine_out) *fine_out = false;
     return GH_OK;
   }
   // Synchronisation rounds until a clean one. Round k makes subsequences 0..k exact whatever the data, so this
@@ -1661,16 +1672,32 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
     g.n_sub = (slice_bytes + g.sub_bytes - 1) / g.sub_bytes;
     const unsigned blocks = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
     if (speculate) {
+#ifdef GH_EXPERIMENTS
       if (fine) {
         int rc = set_fine_attrs();
         if (rc != GH_OK) return rc;
         GH_LAUNCH(dec_fine_speculate_kernel, unsigned((g.n_sub + kFineWarps - 1) / kFineWarps), kFineWarps * 32,
                   sizeof(SmemFineSpec), stream, g, ws);
-      } else {
+      } else
+#endif
         GH_LAUNCH(dec_speculate_kernel, blocks, kDecThreads, 0, stream, g, ws, 0, (const u32*)nullptr, 0u, (u32*)nullptr);
-      }
       int rc = check_launch();
       if (rc != GH_OK) return rc;
+    }
+    if (deferred && speculate && !rewalk && !fine) {
+      // optimistic: one round, offsets, no read-back (see above)
+      h_ctl = DecControl();
+      h_ctl.eof_index = kNoEof;
+      h_ctl.sub_bytes = g.sub_bytes;
+      h_ctl.n_sub = g.n_sub;
+      GH_CUDA_TRY(cudaMemcpyAsync(ws.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, stream));
+      GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
+      int rc = check_launch();
+      if (rc != GH_OK) return rc;
+      *deferred = true;
+      if (geom_out) *geom_out = g;
+      if (fine_out) *fine_out = false;
+      return dec_finish_launch(g, ws, stream, false);
     }
     bool coarsen = false;
     bool have_list = false;  // re-walk rounds: work[cur] lists the subsequences to walk, work_n of them
@@ -1771,17 +1798,20 @@ static int decode_write_impl(const DecGeometry& g, bool fine, uint8_t* d_out, u6
                              cudaStream_t stream) {
   const DecLayout L = dec_layout(g.slice_bits / 8);
   DecWorkspace ws = dec_bind(d_ws, L);
+#ifdef GH_EXPERIMENTS
   if (fine) {
     int rc = set_fine_attrs();
     if (rc != GH_OK) return rc;
     const unsigned blocks = unsigned((g.n_sub + kFineWarps - 1) / kFineWarps);
     GH_LAUNCH(dec_fine_write_kernel, blocks, kFineWarps * 32, sizeof(SmemFineWrite), stream, g, d_out, out_cap, ws);
-  } else {
-    int rc = set_write_attrs();
-    if (rc != GH_OK) return rc;
-    const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
-    GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, sizeof(SmemWrite), stream, g, d_out, out_cap, ws);
+    return check_launch();
   }
+#endif
+  (void)fine;
+  int rc = set_write_attrs();
+  if (rc != GH_OK) return rc;
+  const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
+  GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, sizeof(SmemWrite), stream, g, d_out, out_cap, ws);
   return check_launch();
 }
 
@@ -1791,7 +1821,15 @@ extern "C" {
 
 size_t gh_decode_workspace_bytes(uint64_t payload_bytes) { return gh::dec_layout(payload_bytes).total; }
 
-void gh_debug_select_writer(int pipeline) { gh::g_pipeline = pipeline < 0 || pipeline > 2 ? 0 : pipeline; }
+// test hooks (explicit calls; the library reads no environment variables)
+void gh_debug_select_writer(int pipeline) {
+#ifdef GH_EXPERIMENTS
+  gh::g_pipeline = pipeline < 0 || pipeline > 2 ? 0 : pipeline;
+#else
+  gh::g_pipeline = pipeline == 1 ? 1 : 0;  // the fine pipeline (2) exists in experiment builds only
+#endif
+}
+void gh_debug_disable_phase_walk(int off) { gh::g_no_phase_walk = off != 0; }
 
 int gh_decode_sync(const uint8_t* d_payload, uint64_t slice_bytes, uint64_t readable_bytes, const gh_code* code,
                    uint32_t entry_bit, int first_call, gh_shard_sync* result, void* d_workspace,
@@ -1835,17 +1873,38 @@ namespace gh {
 int decode_full(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code* code, uint32_t entry_bit,
                 uint8_t* d_out, uint64_t out_cap, uint64_t* n_out, void* d_workspace, size_t workspace_bytes,
                 void* stream) {
+  if (!d_out && out_cap) return GH_ERR_ARG;
   gh_shard_sync res;
   DecGeometry g;
-  bool fine = false;
+  bool fine = false, deferred = false;
+  // first attempt: everything enqueued back to back, the control block read once at the end
   int rc = decode_sync_impl(d_payload, payload_bytes, payload_bytes, code, entry_bit, 1, &res, d_workspace,
-                            workspace_bytes, (cudaStream_t)stream, &g, &fine);
+                            workspace_bytes, (cudaStream_t)stream, &g, &fine, &deferred);
   if (rc != GH_OK) return rc;
-  if (n_out) *n_out = res.n_symbols;
-  if (!d_out && out_cap) return GH_ERR_ARG;
   rc = decode_write_impl(g, fine, d_out, out_cap, d_workspace, (cudaStream_t)stream);
   if (rc != GH_OK) return rc;
-  GH_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (deferred) {
+    const DecLayout L = dec_layout(payload_bytes);
+    DecWorkspace ws = dec_bind(d_workspace, L);
+    DecControl h_ctl;
+    rc = dec_read_ctl(ws, &h_ctl, (cudaStream_t)stream);
+    if (rc != GH_OK) return rc;
+    if (h_ctl.changed) {
+      // the single round was not clean: what the writer stored is not final. Again, with as many rounds as it takes.
+      rc = decode_sync_impl(d_payload, payload_bytes, payload_bytes, code, entry_bit, 1, &res, d_workspace, workspace_bytes,
+                            (cudaStream_t)stream, &g, &fine, nullptr);
+      if (rc != GH_OK) return rc;
+      rc = decode_write_impl(g, fine, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+      if (rc != GH_OK) return rc;
+      GH_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    } else {
+      res.n_symbols = h_ctl.total;
+      res.eof_found = h_ctl.eof_found;
+    }
+  } else {
+    GH_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  if (n_out) *n_out = res.n_symbols;
   if (!res.eof_found) return GH_ERR_NO_EOF;
   if (res.n_symbols > out_cap) return GH_ERR_SPACE;
   return GH_OK;

@@ -97,11 +97,8 @@ extern "C" int gh_histogram(const uint8_t* d_in, uint64_t n, uint64_t* d_hist256
   if (n == 0) return GH_OK;
   const int sms = sm_count();
   if (sms <= 0) return cuda_fail(cudaGetLastError());
-  static bool attr_set = false;
-  if (!attr_set) {
-    GH_CUDA_TRY(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
-    attr_set = true;
-  }
+  // per device, hence on every call (it costs nothing)
+  GH_CUDA_TRY(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
   // each thread's u32 counters hold at most the bytes it reads: n / (grid * 224) + 32 < 2^32 needs n < ~1.4e14
   if (n > (1ull << 46)) return GH_ERR_ARG;
   const u64 nvec = n / 16 + 1;

@@ -20,15 +20,14 @@ int cuda_fail(cudaError_t e) {
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    cached = n;
-  }
-  return cached;
+int sm_count() {  // of the CURRENT device (a process may drive several)
+  static std::atomic<int> cached[64];
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64 && (n = cached[dev].load(std::memory_order_relaxed)) > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
+  return n;
 }
 
 // ---- per-kernel timing ------------------------------------------------------------------------------

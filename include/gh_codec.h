@@ -66,10 +66,13 @@ uint64_t gh_launch_count(void);
  * (and resets the counters). Returns the bytes written. Off by default. */
 void gh_profile_enable(int on);
 size_t gh_profile_fetch(char* buf, size_t cap);
-/* Diagnostics only: decode pipeline for A/B measurements -- 0 automatic (currently the coarse
- * thread-per-subsequence pipeline), 1 always coarse, 2 always fine (warp per 2 KiB segment, stored piece states).
- * Output is identical either way. */
+/* Test hooks (explicit calls: the library reads no environment variables). Output is identical either way.
+ * gh_debug_select_writer: 0 automatic, 1 always the thread-per-subsequence pipeline; 2 (warp per 2 KiB segment)
+ * exists only in builds with -DGH_EXPERIMENTS and is ignored otherwise.
+ * gh_debug_disable_phase_walk: non-zero makes codes of 8 and 9 bits take the general re-walk rounds instead of
+ * the phase walk. */
 void gh_debug_select_writer(int pipeline);
+void gh_debug_disable_phase_walk(int off);
 
 /* ------------------------------------------------------------------------------------------------
  * Host: code construction and the file header (microseconds; stays on the host by design)

@@ -320,13 +320,13 @@ def test_emulated_histogram_pipelined_path(emu, oracle):
     assert (hist == oracle.histogram(raw[:n].tobytes())).all()
 
 
-@pytest.mark.parametrize("pipeline", [1, 2])
-def test_emulated_forced_pipelines(emu, ctx, oracle, pipeline):
-    """both decode pipelines forced in turn (1 = coarse thread-per-subsequence, 2 = fine warp-per-segment with stored
-    piece states) give the oracle's bytes on every kind of code, including the ones the automatic choice would
-    route the other way"""
+@pytest.mark.parametrize("mode", ["coarse", "no_phase_walk"])
+def test_emulated_forced_pipelines(emu, ctx, oracle, mode):
+    """the library's test hooks (thread-per-subsequence pipeline forced; phase walk of 8/9-bit codes switched off, so
+    that uniform bytes take the general re-walk rounds) give the oracle's bytes on every kind of code"""
     import golden_huffman_b200.workloads as W
-    emu.lib.gh_debug_select_writer(pipeline)
+    emu.lib.gh_debug_select_writer(1 if mode == "coarse" else 0)
+    emu.lib.gh_debug_disable_phase_walk(1 if mode == "no_phase_walk" else 0)
     try:
         rng = np.random.default_rng(8)
         cases = [make_input("text_small") * 30, W.zipf_np(70001, seed=2).tobytes(),
@@ -337,3 +337,4 @@ def test_emulated_forced_pipelines(emu, ctx, oracle, pipeline):
             _roundtrip(emu, ctx, oracle, data)
     finally:
         emu.lib.gh_debug_select_writer(0)
+        emu.lib.gh_debug_disable_phase_walk(0)

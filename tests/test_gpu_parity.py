@@ -302,12 +302,15 @@ def test_full_size_1gib(codec, oracle, workload):
     assert hashlib.sha256(oimg).digest() == hashlib.sha256(img.cpu().numpy().tobytes()).digest()
 
 
-@pytest.mark.parametrize("pipeline", [1, 2])
-def test_forced_decode_pipelines(codec, oracle, pipeline):
-    """coarse (1) and fine (2) decode pipelines forced in turn: identical output on fast- and slow-synchronising codes"""
+@pytest.mark.parametrize("mode", ["coarse", "no_phase_walk"])
+def test_forced_decode_pipelines(codec, oracle, mode):
+    """the library's test hooks: the thread-per-subsequence pipeline forced, and the phase walk of 8/9-bit codes switched
+    off (uniform bytes then take the general re-walk rounds): identical output on fast- and slow-synchronising codes"""
     import torch
     import golden_huffman_b200.workloads as w
-    codec.lib.lib.gh_debug_select_writer(pipeline)
+    pipeline = mode
+    codec.lib.lib.gh_debug_select_writer(1 if mode == "coarse" else 0)
+    codec.lib.lib.gh_debug_disable_phase_walk(1 if mode == "no_phase_walk" else 0)
     try:
         for name in ("zipf", "uniform", "skewed", "text"):
             n = (1 << 23) + 77
@@ -321,6 +324,7 @@ def test_forced_decode_pipelines(codec, oracle, pipeline):
         assert rc == 0 and nd == len(data) and _bytes(out) == data
     finally:
         codec.lib.lib.gh_debug_select_writer(0)
+        codec.lib.lib.gh_debug_disable_phase_walk(0)
 
 
 @pytest.mark.gpu

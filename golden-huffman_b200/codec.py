@@ -49,6 +49,8 @@ class Codec:
     def _check_u8(self, x):
         assert x.dtype == torch.uint8 and x.device == self.device and x.is_contiguous(), \
             "expected a contiguous uint8 tensor on the codec's device"
+        assert x.data_ptr() % 16 == 0, "the kernels read and write 128-bit vectors: the tensor's storage must start on a " \
+                                       "16-byte boundary (a slice such as x[1:] does not; copy it first)"
 
     # ---- the path, step by step -------------------------------------------------------------------------
     def histogram(self, x, out=None, accumulate=False):

@@ -86,6 +86,7 @@ void gh_ctx_destroy(gh_ctx* c) {
 int gh_compress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, uint64_t* out_bytes) {
   using namespace gh;
   if (!c || !d_out || !out_bytes) return GH_ERR_ARG;
+  c->staged_n = c->staged_payload = 0;  // the context's buffers are about to be reused: nothing stays staged
   if (n == 0) return GH_ERR_EMPTY;
   if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) return GH_ERR_ARG;
   // 1. histogram (Encoder::caculate_frequency), counters back to the host
@@ -125,6 +126,7 @@ int gh_compress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_ou
 int gh_decompress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, uint64_t* out_bytes) {
   using namespace gh;
   if (!c || !d_in || !out_bytes || (!d_out && cap)) return GH_ERR_ARG;
+  c->staged_n = c->staged_payload = 0;  // the context's buffers are about to be reused: nothing stays staged
   if (reinterpret_cast<uintptr_t>(d_in) & 15) return GH_ERR_ARG;
   // 1. header (get_encode_info)
   const size_t peek = n < kMaxHeader ? size_t(n) : kMaxHeader;
@@ -148,6 +150,7 @@ int gh_decompress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_
 int gh_compress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
   using namespace gh;
   if (!c || !out || !out_bytes) return GH_ERR_ARG;
+  c->staged_n = c->staged_payload = 0;  // the context's buffers are about to be reused: nothing stays staged
   if (n == 0) return GH_ERR_EMPTY;
   if (!in) return GH_ERR_ARG;
   int rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, n + 16);
@@ -171,6 +174,7 @@ int gh_compress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uin
 int gh_decompress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
   using namespace gh;
   if (!c || !in || !out_bytes || (!out && cap)) return GH_ERR_ARG;
+  c->staged_n = c->staged_payload = 0;  // the context's buffers are about to be reused: nothing stays staged
   int rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, n + 16);
   if (rc != GH_OK) return rc;
   GH_CUDA_TRY(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));

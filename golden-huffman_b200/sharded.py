@@ -15,12 +15,14 @@ encode, rank r of W holding input slice x_r:
   Rank r then owns global payload bytes [ceil(S_r / 8), ceil(S_{r+1} / 8)).
 
 decode, rank r holding its byte range of the payload:
-  1. slices are re-cut at 16-byte boundaries of the global stream (only byte offsets are needed for that) and
-     each rank fetches a 32-byte halo from its right neighbour
-  2. every rank self-synchronises its slice assuming its first codeword starts at bit 0 (gh_decode_sync)
-  3. all_gather of (exit_bit, n_symbols, eof) per rank; a rank whose left neighbour's exit_bit differs from
-     the entry it assumed re-synchronises (only the affected subsequences are walked) -- repeated until no
-     entry changes
+  1. slices are re-cut at 16-byte boundaries of the global stream (only byte offsets are needed for that); in ONE
+     neighbour exchange each rank fetches a 32-byte halo from its right neighbour and the 4 KiB that precede its
+     slice from its left neighbour
+  2. every rank first walks those 4 KiB from an arbitrary bit (a self-synchronising code has found the true
+     codeword boundaries long before the end of them): where that walk leaves the halo is, almost surely, where the
+     slice's first codeword starts. Then it self-synchronises its slice from there (gh_decode_sync)
+  3. ONE all_gather of (exit_bit, n_symbols, eof, entry) per rank confirms that every rank's entry is its left
+     neighbour's exit; only if one is not (never observed) the stale ranks re-synchronise and the gather repeats
   4. exclusive scan of the symbol counts -> each rank's output offset; gh_decode_write; output stays sharded.
 
 Collectives are tiny (KiB) and latency-bound; bulk data never crosses NVLink."""
@@ -28,7 +30,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-HALO = 32
+HALO = 32          # bytes fetched from the right neighbour (a codeword may straddle the slice end)
+LEFT_HALO = 4096   # bytes before the slice start that are walked to find the slice's first codeword
+HEAD = 8192        # room in front of the payload buffer for the left halo
 
 
 def _ceil_div(a, b):
@@ -48,8 +52,10 @@ class ShardedCodec:
     def prepare(self, n_local_max):
         """allocate per-rank buffers once: worst-case payload for n_local_max input bytes"""
         cap = self.lib.compress_bound(n_local_max) + 256
+        full = torch.empty(HEAD + cap, dtype=torch.uint8, device=self.dev)
         return {
-            "payload": torch.empty(cap, dtype=torch.uint8, device=self.dev),
+            "payload_full": full,
+            "payload": full[HEAD:],
             "out": torch.empty(n_local_max + 4096, dtype=torch.uint8, device=self.dev),
             "hists": torch.empty(self.world * 256, dtype=torch.int64, device=self.dev),
             "hist": torch.empty(256, dtype=torch.int64, device=self.dev),
@@ -59,6 +65,7 @@ class ShardedCodec:
             "halo": torch.zeros(HALO, dtype=torch.uint8, device=self.dev),
             "meta": torch.zeros(self.world * 4, dtype=torch.int64, device=self.dev),
             "mine": torch.zeros(4, dtype=torch.int64, device=self.dev),
+            "mine_host": torch.zeros(4, dtype=torch.int64).pin_memory() if self.dev.type == "cuda" else torch.zeros(4, dtype=torch.int64),
         }
 
     # ---- encode -------------------------------------------------------------------------------------------
@@ -70,6 +77,8 @@ class ShardedCodec:
         c.histogram(x, out=st["hist"])
         dist.all_gather_into_tensor(st["hists"], st["hist"], group=self.group)
         hists = st["hists"].cpu().numpy().astype(np.uint64).reshape(W, 256)  # one D2H, also the sync point
+        if (hists.sum(axis=1) == 0).any():  # decided from the gathered data: every rank raises together
+            raise ValueError("sharded compress: a rank holds an empty slice")
         code = lib.build_code(hists.sum(axis=0))
         bits = [lib.payload_bits(code, hists[q], with_eof=(q == W - 1)) for q in range(W)]
         starts = np.concatenate([[0], np.cumsum(bits)]).astype(object)  # python ints: no overflow
@@ -95,7 +104,8 @@ class ShardedCodec:
         last = _ceil_div(E, 8)
         total_bytes = _ceil_div(int(starts[W]), 8)
         header = lib.write_header(code) if r == 0 else None
-        return {"code": code, "header": header, "payload": payload, "base_byte": base_byte, "first_byte": first,
+        return {"code": code, "header": header, "payload": payload, "payload_full": st["payload_full"], "start_bit": S,
+                "base_byte": base_byte, "first_byte": first,
                 "end_byte": last, "payload_bytes": last - first, "total_bytes": total_bytes,
                 "byte_starts": [(_ceil_div(int(starts[q]), 8) if q > 0 else 0) for q in range(W)] + [total_bytes]}
 
@@ -109,20 +119,31 @@ class ShardedCodec:
         # slice boundaries: owned-range starts rounded up to 16 bytes of the global stream
         cuts = [0] + [min(total, _ceil_div(byte_starts[q], 16) * 16) for q in range(1, W)] + [total]
         a, b = cuts[r], cuts[r + 1]
-        # halo: the right neighbour's first HALO owned bytes, appended after our owned range
+        if any(cuts[q + 1] - cuts[q] < 16 for q in range(W)):  # same data on every rank: they raise together
+            raise ValueError("sharded decode: a rank's slice of the payload is shorter than 16 bytes")
+        own = [byte_starts[q + 1] - byte_starts[q] for q in range(W)]
+        # the left halo is used when every rank can serve it from its own bytes (else: entry guess 0 and rounds)
+        use_left = all(own[q] >= LEFT_HALO + HALO and cuts[q + 1] - LEFT_HALO >= byte_starts[q] for q in range(W - 1))
+        full, base = enc["payload_full"], enc["base_byte"] - HEAD  # full[i] holds global byte base + i
+        # one neighbour exchange: right halo (the right neighbour's first HALO owned bytes, appended after our owned
+        # range) and left halo (the bytes between cuts[r] - LEFT_HALO and our first owned byte)
         ops = []
         if r > 0:
-            lo = byte_starts[r] - enc["base_byte"]
-            ops.append(dist.P2POp(dist.isend, payload[lo:lo + HALO], r - 1, group=self.group))
+            lo = byte_starts[r] - base
+            ops.append(dist.P2POp(dist.isend, full[lo:lo + HALO], r - 1, group=self.group))
+            if use_left:
+                ops.append(dist.P2POp(dist.irecv, full[cuts[r] - LEFT_HALO - base: byte_starts[r] - base], r - 1, group=self.group))
         if r < W - 1:
             ops.append(dist.P2POp(dist.irecv, st["halo"], r + 1, group=self.group))
+            if use_left:
+                ops.append(dist.P2POp(dist.isend, full[cuts[r + 1] - LEFT_HALO - base: byte_starts[r + 1] - base], r + 1, group=self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         if r < W - 1:
-            hi = enc["end_byte"] - enc["base_byte"]
-            payload[hi:hi + HALO].copy_(st["halo"])
-        ptr = payload.data_ptr() + (a - enc["base_byte"])
+            hi = enc["end_byte"] - base
+            full[hi:hi + HALO].copy_(st["halo"])
+        ptr = full.data_ptr() + (a - base)
         slice_bytes = b - a
         readable = slice_bytes + (8 if r < W - 1 else 0)
         ws = st["dec_ws"]
@@ -130,10 +151,15 @@ class ShardedCodec:
         wbytes = ws.numel() - 256
         stream = c._stream()
         entry = 0  # the first-codeword position this rank currently assumes for its slice
+        if use_left and r > 0:
+            walk = lib.decode_sync(ptr - LEFT_HALO, LEFT_HALO, LEFT_HALO + 8, code, 0, True, wptr, wbytes, stream)
+            entry = int(walk.exit_bit)
         res = lib.decode_sync(ptr, slice_bytes, readable, code, entry, True, wptr, wbytes, stream)
         rounds = 0
+        mine_host = st["mine_host"]
         while True:
-            st["mine"].copy_(torch.tensor([res.exit_bit, res.n_symbols, res.eof_found, entry], dtype=torch.int64))
+            mine_host[0], mine_host[1], mine_host[2], mine_host[3] = int(res.exit_bit), int(res.n_symbols), int(res.eof_found), entry
+            st["mine"].copy_(mine_host, non_blocking=True)
             dist.all_gather_into_tensor(st["meta"], st["mine"], group=self.group)
             meta = st["meta"].cpu().numpy().reshape(W, 4)
             rounds += 1
@@ -154,7 +180,8 @@ class ShardedCodec:
             raise RuntimeError("sharded decode: output buffer too small for this rank's slice")
         lib.decode_write(ptr, slice_bytes, readable, code, out.data_ptr(), n_sym, wptr, wbytes, stream)
         offset = sum(counts[q] for q in range(r) if q <= first_eof)
-        self.last_decode = {"rounds": rounds, "offset": offset, "counts": counts, "first_eof": first_eof, "cuts": cuts}
+        self.last_decode = {"rounds": rounds, "offset": offset, "counts": counts, "first_eof": first_eof, "cuts": cuts,
+                            "left_halo": bool(use_left)}
         return out[:n_sym], n_sym
 
     # ---- verification helper (not part of the codec path) -----------------------------------------------

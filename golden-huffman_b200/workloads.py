@@ -15,8 +15,10 @@ def _zipf_pmf(s=ZIPF_S, k=256):
     return p / p.sum()
 
 
-def _rank_to_byte(seed=SEED):
-    return np.random.default_rng(seed).permutation(256).astype(np.uint8)
+def _rank_to_byte():
+    """the Zipf rank -> byte value permutation: part of the DISTRIBUTION, so it is fixed (SEED) whatever seed draws
+    the samples -- the shards of a multi-GPU run are then samples of one and the same distribution"""
+    return np.random.default_rng(SEED).permutation(256).astype(np.uint8)
 
 
 def _english_pmf():
@@ -55,7 +57,7 @@ def _sample_pmf_np(n, pmf, table, seed, chunk=1 << 24):
 
 
 def zipf_np(n, seed=SEED):
-    return _sample_pmf_np(n, _zipf_pmf(), _rank_to_byte(seed), seed)
+    return _sample_pmf_np(n, _zipf_pmf(), _rank_to_byte(), seed)
 
 
 def uniform_np(n, seed=SEED):
@@ -73,10 +75,17 @@ def fib_counts(k=31):
     return f[:k]
 
 
-def skewed_np(n, seed=SEED, k=31):
+def shard_fib_counts(rank=0, world=1, k=31):
+    """this shard's share of the Fibonacci counts: the counts of the WHOLE input are Fibonacci(i) whatever the
+    number of shards (symbol i's occurrences are dealt round-robin, starting at rank i % world)"""
+    return [c // world + (1 if (rank - i) % world < c % world else 0) for i, c in enumerate(fib_counts(k))]
+
+
+def skewed_np(n, seed=SEED, k=31, rank=0, world=1):
     """bytes 0..k-1 occur Fibonacci(i) times, byte k fills the rest -> k+2 symbols with the end mark, and for
-    k = 31 a maximum code length of exactly 32; positions are shuffled."""
-    f = fib_counts(k)
+    k = 31 a maximum code length of exactly 32; positions are shuffled.
+    With world > 1 this is shard `rank` of such an input of world * n bytes."""
+    f = shard_fib_counts(rank, world, k)
     total = sum(f)
     assert n > total, f"need n > {total}"
     out = np.full(n, k, dtype=np.uint8)
@@ -106,7 +115,7 @@ def _sample_pmf_torch(n, pmf, table, device, seed, chunk=1 << 26):
 
 
 def zipf_torch(n, device, seed=SEED):
-    return _sample_pmf_torch(n, _zipf_pmf(), _rank_to_byte(seed), device, seed)
+    return _sample_pmf_torch(n, _zipf_pmf(), _rank_to_byte(), device, seed)
 
 
 def uniform_torch(n, device, seed=SEED):
@@ -125,9 +134,9 @@ def text_torch(n, device, seed=SEED):
     return _sample_pmf_torch(n, _english_pmf(), np.arange(256, dtype=np.uint8), device, seed)
 
 
-def skewed_torch(n, device, seed=SEED, k=31):
+def skewed_torch(n, device, seed=SEED, k=31, rank=0, world=1):
     import torch
-    f = fib_counts(k)
+    f = shard_fib_counts(rank, world, k)
     total = sum(f)
     assert n > total
     g = torch.Generator(device=device)

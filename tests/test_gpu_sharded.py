@@ -56,19 +56,21 @@ def _worker(rank, world, port, n_total, kind, q):
             dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["text", "uniform", "skewed"])
-def test_sharded_roundtrip_nccl(kind):
+@pytest.mark.parametrize("kind,n_total", [("text", (48 << 20) + 12345), ("uniform", (48 << 20) + 12345),
+                                          ("skewed", (48 << 20) + 12345), ("text", 1 << 30)])
+def test_sharded_roundtrip_nccl(kind, n_total):
+    """every rank's owned payload bytes == the oracle's stream for the whole input (the last case: 1 GiB in total),
+    decoded slices == the input"""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 1000)
-    n_total = (48 << 20) + 12345
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, kind, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=900) for _ in procs]
+    results = [q.get(timeout=1500) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     for rank, status, info in results:

@@ -65,7 +65,7 @@ def _worker(rank, world, port, n_per_rank, kind, q):
         sums = torch.tensor([nsym], dtype=torch.int64)
         dist.all_reduce(sums)
         assert int(sums.item()) == total
-        q.put((rank, "ok", sc.last_decode["rounds"]))
+        q.put((rank, "ok", (sc.last_decode["rounds"], sc.last_decode["left_halo"])))
     except Exception as e:  # pragma: no cover
         import traceback
         q.put((rank, "fail", traceback.format_exc()))
@@ -74,14 +74,18 @@ def _worker(rank, world, port, n_per_rank, kind, q):
             dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kind", [(2, "text"), (3, "zipf"), (2, "uniform")])
-def test_sharded_roundtrip_gloo(world, kind):
+@pytest.mark.parametrize("world,kind,n_per_rank", [(2, "text", 20000), (3, "zipf", 20000), (2, "uniform", 20000),
+                                                   (3, "text", 3000)])
+def test_sharded_roundtrip_gloo(world, kind, n_per_rank):
+    """per-rank payload bytes == the oracle's stream, decoded slices == the input. With shards of 20000 bytes every
+    rank finds its first codeword by walking the 4 KiB before its slice (one gather confirms it for codes that
+    synchronise quickly); with 3000-byte shards there is no room for that halo and the entries are found by rounds."""
     import emul_lib
     emul_lib.load()  # build once, before forking
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 20000, kind, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + world + (7 if n_per_rank < 20000 else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_per_rank, kind, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]
@@ -89,3 +93,7 @@ def test_sharded_roundtrip_gloo(world, kind):
         p.join(timeout=60)
     for rank, status, info in results:
         assert status == "ok", f"rank {rank}: {info}"
+        rounds, left = info
+        assert left == (n_per_rank >= 20000)
+        if left and kind != "uniform":
+            assert rounds == 1, f"rank {rank}: {rounds} gather rounds with the left halo"

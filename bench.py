@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-mib", type=int, default=256)
     ap.add_argument("--no-named-config", action="store_true", help="N > 1: skip the BASELINE config named for this N")
+    ap.add_argument("--device-code", type=int, default=-1, help="1/0: build the code on the device / on the host (default: the library's default)")
     ap.add_argument("--named-steps", type=int, default=5)
     return ap.parse_args()
 
@@ -354,6 +355,8 @@ def main():
     codec = gh.Codec(lib)
     stream = torch.cuda.current_stream()
     lib.ctx_set_stream(codec.ctx, stream.cuda_stream)
+    if args.device_code >= 0:
+        lib.ctx_set_device_code(codec.ctx, bool(args.device_code))
 
     n = args.size_mib << 20
     res = measure(args, lib, codec, W, dist, dev, rank, world, args.workload, n, args.steps, args.warmup, True)

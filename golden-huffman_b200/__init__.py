@@ -10,7 +10,7 @@ Layout
 
 PyTorch is used for device memory, streams and torch.distributed only; every byte of codec work happens in
 lib/libgh_b200.so, and importing fails loudly if that library has not been built."""
-from .capi import GhLib, GhCode, GhError, GhShardSync, DEFAULT_LIB, SIGNATURES  # noqa: F401
+from .capi import GhLib, GhCode, GhDeviceCode, GhError, GhShardSync, DEFAULT_LIB, SIGNATURES  # noqa: F401
 from .codec import Codec  # noqa: F401
 
-__all__ = ["GhLib", "GhCode", "GhError", "GhShardSync", "Codec", "DEFAULT_LIB", "SIGNATURES"]
+__all__ = ["GhLib", "GhCode", "GhDeviceCode", "GhError", "GhShardSync", "Codec", "DEFAULT_LIB", "SIGNATURES"]

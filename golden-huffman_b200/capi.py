@@ -27,6 +27,23 @@ class GhCode(C.Structure):
     ]
 
 
+class GhEncodeTable(C.Structure):
+    _fields_ = [("codeword", C.c_uint32 * NSYM), ("length", C.c_uint8 * (NSYM + 3))]
+
+
+class GhDeviceCode(C.Structure):
+    """struct gh_device_code: what gh_build_code_device leaves in device memory"""
+    _fields_ = [
+        ("code", GhCode),
+        ("status", C.c_uint32),
+        ("header_bytes", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("payload_bits", C.c_uint64),
+        ("total_symbols", C.c_uint64),
+        ("table", GhEncodeTable),
+    ]
+
+
 class GhShardSync(C.Structure):
     _fields_ = [
         ("n_symbols", C.c_uint64),
@@ -55,6 +72,8 @@ SIGNATURES = {
     "gh_debug_select_writer": (None, [_INT]),
     "gh_debug_disable_phase_walk": (None, [_INT]),
     "gh_ctx_set_stream": (_INT, [_VP, _VP]),
+    "gh_ctx_set_device_code": (_INT, [_VP, _INT]),
+    "gh_build_code_device": (_INT, [_VP, _INT, _VP, _VP, _VP]),
     "gh_build_code": (_INT, [_VP, _CODEP]),
     "gh_header_bytes": (_SZ, [_CODEP]),
     "gh_write_header": (_INT, [_CODEP, _VP, _SZ, C.POINTER(_SZ)]),
@@ -136,6 +155,13 @@ class GhLib:
         code = GhCode()
         self.check(self.lib.gh_build_code(h.ctypes.data, C.byref(code)), "gh_build_code")
         return code
+
+    def build_code_device(self, d_hists, n_hists, d_code, d_header=0, stream=0):
+        """device pointers: n_hists x 256 u64 counters in, struct gh_device_code (and optionally the header) out"""
+        self.check(self.lib.gh_build_code_device(d_hists, n_hists, d_code, d_header, stream), "gh_build_code_device")
+
+    def ctx_set_device_code(self, ctx, on=True):
+        self.check(self.lib.gh_ctx_set_device_code(ctx, 1 if on else 0), "gh_ctx_set_device_code")
 
     def header_bytes(self, code):
         return int(self.lib.gh_header_bytes(C.byref(code)))

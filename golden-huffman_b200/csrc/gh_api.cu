@@ -1,6 +1,7 @@
 // Whole ".crs2" images: what Compressor<CanonicalHuffEncoder<> >::compress() and
 // Decompressor<CanonicalHuffDecoder<> >::decompress() (reference include/compressor.h:62-73, 87-92) do for a
 // file, minus the file I/O. Device-resident variants (kernels only) and host-buffer variants (H2D + kernels + D2H).
+#include <stddef.h>
 #include <string.h>
 
 #include "gh_common.cuh"
@@ -16,6 +17,8 @@ struct gh_ctx {
   size_t ws_cap;
   uint64_t* d_small;  // 256 histogram counters + end bit
   uint8_t* h_small;   // pinned: histogram read-back, header staging
+  gh_device_code* d_code;  // code built on the device (gh_ctx_set_device_code)
+  bool device_code;
   // state of the staged (step-by-step) entry points
   uint64_t staged_n;         // input bytes resident in d_in (gh_stage_input)
   uint64_t staged_payload;   // payload bytes resident in d_in (gh_stage_payload)
@@ -54,6 +57,7 @@ int gh_ctx_create(gh_ctx** out) {
   memset(c, 0, sizeof(*c));
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&c->d_small), kSmallBytes) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&c->d_code), sizeof(gh_device_code)) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&c->h_small), kSmallBytes) != cudaSuccess) {
     const int rc = cuda_fail(cudaGetLastError());
     gh_ctx_destroy(c);
@@ -72,12 +76,19 @@ int gh_ctx_set_stream(gh_ctx* c, void* stream) {
   return GH_OK;
 }
 
+int gh_ctx_set_device_code(gh_ctx* c, int on) {
+  if (!c) return GH_ERR_ARG;
+  c->device_code = on != 0;
+  return GH_OK;
+}
+
 void gh_ctx_destroy(gh_ctx* c) {
   if (!c) return;
   if (c->d_in) cudaFree(c->d_in);
   if (c->d_out) cudaFree(c->d_out);
   if (c->d_ws) cudaFree(c->d_ws);
   if (c->d_small) cudaFree(c->d_small);
+  if (c->d_code) cudaFree(c->d_code);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -89,9 +100,35 @@ int gh_compress_device(gh_ctx* c, const uint8_t* d_in, uint64_t n, uint8_t* d_ou
   c->staged_n = c->staged_payload = 0;  // the context's buffers are about to be reused: nothing stays staged
   if (n == 0) return GH_ERR_EMPTY;
   if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) return GH_ERR_ARG;
-  // 1. histogram (Encoder::caculate_frequency), counters back to the host
+  // 1. histogram (Encoder::caculate_frequency)
   int rc = gh_histogram(d_in, n, c->d_small, 0, c->stream);
   if (rc != GH_OK) return rc;
+  if (c->device_code) {
+    // 2.-3. code, header and payload without the host: K1 -> build_code_kernel -> packer, one read-back at the end
+    rc = gh_build_code_device(c->d_small, 1, c->d_code, d_out, c->stream);
+    if (rc != GH_OK) return rc;
+    rc = grow(&c->d_ws, &c->ws_cap, gh_encode_workspace_bytes(n));
+    if (rc != GH_OK) return rc;
+    uint64_t* d_end = c->d_small + 256;
+    rc = encode_with_device_code(d_in, n, c->d_code, d_out, cap, d_end, c->d_ws, c->ws_cap, c->stream);
+    if (rc != GH_OK) return rc;
+    struct Tail {  // gh_device_code from `status` on
+      uint32_t status, header_bytes, reserved;
+      uint32_t payload_bits_lo, payload_bits_hi;  // (the struct's 64-bit fields are 8-byte aligned, `status` is not)
+    };
+    static_assert(offsetof(gh_device_code, payload_bits) - offsetof(gh_device_code, status) == offsetof(Tail, payload_bits_lo),
+                  "Tail mirrors gh_device_code");
+    Tail* h_tail = reinterpret_cast<Tail*>(c->h_small);
+    GH_CUDA_TRY(cudaMemcpyAsync(h_tail, &c->d_code->status, sizeof(Tail), cudaMemcpyDeviceToHost, c->stream));
+    GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h_tail->status != uint32_t(GH_OK)) return int(h_tail->status);
+    const uint64_t payload_bits = (uint64_t(h_tail->payload_bits_hi) << 32) | h_tail->payload_bits_lo;
+    const uint64_t bytes = uint64_t(h_tail->header_bytes) + (payload_bits + 7) / 8;
+    if (cap < (bytes + 3) / 4 * 4) return GH_ERR_SPACE;  // the packer's stores were bounded by cap
+    *out_bytes = bytes;
+    return GH_OK;
+  }
+  // 2. counters back to the host
   uint64_t* h_hist = reinterpret_cast<uint64_t*>(c->h_small);
   GH_CUDA_TRY(cudaMemcpyAsync(h_hist, c->d_small, 256 * 8, cudaMemcpyDeviceToHost, c->stream));
   GH_CUDA_TRY(cudaStreamSynchronize(c->stream));

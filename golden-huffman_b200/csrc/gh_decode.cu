@@ -1684,20 +1684,42 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
       int rc = check_launch();
       if (rc != GH_OK) return rc;
     }
-    if (deferred && speculate && !rewalk && !fine) {
-      // optimistic: one round, offsets, no read-back (see above)
+    if (!rewalk && !fine && !coarsened) {
+      // Optimistic first round: one synchronisation round and the offset kernels are enqueued together and the control
+      // block is read back ONCE (or not at all here, when the caller defers it). A self-synchronising code is at its
+      // fixed point after that round; if an exit did move, the rounds below take over.
       h_ctl = DecControl();
       h_ctl.eof_index = kNoEof;
       h_ctl.sub_bytes = g.sub_bytes;
       h_ctl.n_sub = g.n_sub;
       GH_CUDA_TRY(cudaMemcpyAsync(ws.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, stream));
-      GH_LAUNCH(dec_sync_kernel, blocks, kDecThreads, 0, stream, g, ws);
+      // re-entry with a corrected first-codeword position: staleness only travels rightwards through exits that
+      // move, so the first round needs the first block only
+      const unsigned first_blocks = (!first_call && !speculate) ? 1u : blocks;
+      GH_LAUNCH(dec_sync_kernel, first_blocks, kDecThreads, 0, stream, g, ws);
       int rc = check_launch();
+      if (rc == GH_OK) rc = dec_finish_launch(g, ws, stream, false);
       if (rc != GH_OK) return rc;
-      *deferred = true;
       if (geom_out) *geom_out = g;
       if (fine_out) *fine_out = false;
-      return dec_finish_launch(g, ws, stream, false);
+      if (deferred) {
+        *deferred = true;
+        return GH_OK;
+      }
+      rc = dec_read_ctl(ws, &h_ctl, stream);
+      if (rc != GH_OK) return rc;
+      ++rounds;
+      if (!h_ctl.changed) {
+        if (result) {
+          result->n_symbols = h_ctl.total;
+          result->exit_bit = h_ctl.exit_bit;
+          result->eof_found = h_ctl.eof_found;
+          result->rounds = rounds;
+          result->sub_bytes = g.sub_bytes;
+        }
+        return GH_OK;
+      }
+      if (u64(h_ctl.exits_changed) * 10 > g.n_sub) rewalk = true;  // the paths do not meet early with this code
     }
     bool coarsen = false;
     bool have_list = false;  // re-walk rounds: work[cur] lists the subsequences to walk, work_n of them

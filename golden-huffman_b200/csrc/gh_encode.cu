@@ -293,10 +293,20 @@ __device__ __forceinline__ void enc_clear(u32* buf, u32 tile_bits, u32 t) {
 }
 
 __global__ void __launch_bounds__(kEncThreads, 1)
-encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u64 start_bit, int append_eof,
-              u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out, EncWorkspace ws,
-              u32 smem_bytes) {
+encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable* __restrict__ tablep, const gh_device_code* __restrict__ dyn,
+              u64 start_bit, int append_eof, u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out,
+              EncWorkspace ws, u32 smem_bytes) {
   GH_DYNAMIC_SMEM(smem_raw);
+  if (dyn) {
+    // the code was built on the device: the payload follows the header build_code_kernel wrote, and is packed from the
+    // 32-byte boundary below the header's end on (the decoder reads whole 32-byte sectors from there)
+    if (dyn->status != u32(GH_OK)) return;
+    const u32 hdr = dyn->header_bytes, base = hdr & ~31u;
+    out_words += base / 4;
+    out_word_cap = out_word_cap > base / 4 ? out_word_cap - base / 4 : 0;
+    start_bit = u64(hdr - base) * 8;
+  }
+  const EncodeTable& table = *tablep;
   const unsigned group = threadIdx.x / kEncGroupThreads, tg = threadIdx.x % kEncGroupThreads;
   const unsigned lane = tg & 31, wg = tg >> 5;
 
@@ -511,9 +521,16 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table, u6
 // Second kernel: OR each tile's deferred head bits into the word its predecessor stored.
 // Thread = tile. The first tile (in order) holding head bits for a given word merges the whole run.
 __global__ void __launch_bounds__(256)
-encode_stitch_kernel(u64 ntiles, u32* __restrict__ out_words, u64 out_word_cap, EncWorkspace ws) {
+encode_stitch_kernel(u64 ntiles, const gh_device_code* __restrict__ dyn, u32* __restrict__ out_words, u64 out_word_cap,
+                     EncWorkspace ws) {
   const u64 tile = u64(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tile == 0 || tile >= ntiles) return;
+  if (dyn) {  // same placement as encode_kernel
+    if (dyn->status != u32(GH_OK)) return;
+    const u32 base = dyn->header_bytes & ~31u;
+    out_words += base / 4;
+    out_word_cap = out_word_cap > base / 4 ? out_word_cap - base / 4 : 0;
+  }
   const u64 g = ws.tile_state[tile - 1] & ~kFlagMask;  // global start bit of `tile`
   if ((g & 31) == 0) return;                            // starts on a word boundary: nothing deferred
   const u64 word = g >> 5;
@@ -530,9 +547,10 @@ encode_stitch_kernel(u64 ntiles, u32* __restrict__ out_words, u64 out_word_cap, 
   if (word < out_word_cap) out_words[word] |= be32(bits);
 }
 
+constexpr size_t kEncTableSlot = 2048;  // the encode table, in front of the workspace, when it comes from the host
 inline size_t enc_ws_bytes(u64 n) {
   const u64 nt = enc_num_tiles(n) + 1;
-  return size_t(nt * 8 + ((nt * 4 + 7) / 8) * 8 + 256);
+  return kEncTableSlot + size_t(nt * 8 + ((nt * 4 + 7) / 8) * 8 + 256);
 }
 
 }  // namespace gh
@@ -559,6 +577,44 @@ int gh_encode(const uint8_t* d_in, uint64_t n, const gh_code* code, uint64_t sta
 
 namespace gh {
 
+// the launches shared by both entry points: the table is at d_table (device), `dyn` tells the kernels to place the
+// payload behind a device-written header
+static int encode_launch(const uint8_t* d_in, u64 n, const EncodeTable* d_table, const gh_device_code* dyn, u64 start_bit,
+                         int append_eof, uint8_t* d_payload, u64 payload_cap, u64* d_end_bit, uint8_t* ws_bytes_ptr, void* stream) {
+  const u64 ntiles = enc_num_tiles(n);
+  if (ntiles > 0x7ffffff0ull) return GH_ERR_ARG;
+  EncWorkspace ws;
+  uint8_t* p = ws_bytes_ptr;
+  ws.tile_state = reinterpret_cast<u64*>(p);
+  p += (ntiles + 1) * 8;
+  ws.head = reinterpret_cast<u32*>(p);
+  p += (((ntiles + 1) * 4 + 7) / 8) * 8;
+  ws.ticket = reinterpret_cast<u32*>(p);
+  const size_t used = size_t(p - ws_bytes_ptr) + 8;
+  GH_CUDA_TRY(cudaMemsetAsync(ws_bytes_ptr, 0, used, (cudaStream_t)stream));
+
+  // all of the SM's shared memory: the table's fixed window address decides the layout (see the kernel)
+  int dev = 0, smem_max = 0;
+  GH_CUDA_TRY(cudaGetDevice(&dev));
+  GH_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  const u64 out_word_cap = payload_cap / 4;
+  // persistent: one CTA per SM, four tile-taking groups each
+  u64 blocks = u64(sm_count() > 0 ? sm_count() : 1);
+  const u64 want = (ntiles + kEncGroups - 1) / kEncGroups;
+  if (blocks > want) blocks = want;
+  GH_LAUNCH(encode_kernel, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, d_table, dyn, (u64)start_bit,
+            append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, d_end_bit, ws, u32(smem_max));
+  int rc = check_launch();
+  if (rc != GH_OK) return rc;
+  if (ntiles > 1) {
+    GH_LAUNCH(encode_stitch_kernel, unsigned((ntiles + 255) / 256), 256, 0, stream, ntiles, dyn,
+              reinterpret_cast<u32*>(d_payload), out_word_cap, ws);
+    rc = check_launch();
+  }
+  return rc;
+}
+
 int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint64_t start_bit, int append_eof,
                      uint8_t* d_payload, uint64_t payload_cap, uint64_t* d_end_bit, void* d_workspace,
                      size_t workspace_bytes, void* stream) {
@@ -572,39 +628,23 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   EncodeTable table;
   int rc = build_encode_table(code, &table);
   if (rc != GH_OK) return rc;
-  const u64 ntiles = enc_num_tiles(n);
-  if (ntiles > 0x7ffffff0ull) return GH_ERR_ARG;
+  // the table travels to the front of the workspace (pageable source: the copy is staged before this call returns)
+  uint8_t* const w = static_cast<uint8_t*>(d_workspace);
+  GH_CUDA_TRY(cudaMemcpyAsync(w, &table, sizeof(table), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return encode_launch(d_in, n, reinterpret_cast<const EncodeTable*>(w), nullptr, start_bit, append_eof, d_payload, payload_cap,
+                       reinterpret_cast<u64*>(d_end_bit), w + kEncTableSlot, stream);
+}
 
-  EncWorkspace ws;
-  uint8_t* p = static_cast<uint8_t*>(d_workspace);
-  ws.tile_state = reinterpret_cast<u64*>(p);
-  p += (ntiles + 1) * 8;
-  ws.head = reinterpret_cast<u32*>(p);
-  p += (((ntiles + 1) * 4 + 7) / 8) * 8;
-  ws.ticket = reinterpret_cast<u32*>(p);
-  const size_t used = size_t(p - static_cast<uint8_t*>(d_workspace)) + 8;
-  GH_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, used, (cudaStream_t)stream));
-
-  // all of the SM's shared memory: the table's fixed window address decides the layout (see the kernel)
-  int dev = 0, smem_max = 0;
-  GH_CUDA_TRY(cudaGetDevice(&dev));
-  GH_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-  const u64 out_word_cap = payload_cap / 4;
-  // persistent: one CTA per SM, four tile-taking groups each
-  u64 blocks = u64(sm_count() > 0 ? sm_count() : 1);
-  const u64 want = (ntiles + kEncGroups - 1) / kEncGroups;
-  if (blocks > want) blocks = want;
-  GH_LAUNCH(encode_kernel, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, (u64)start_bit,
-            append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, reinterpret_cast<u64*>(d_end_bit), ws, u32(smem_max));
-  rc = check_launch();
-  if (rc != GH_OK) return rc;
-  if (ntiles > 1) {
-    GH_LAUNCH(encode_stitch_kernel, unsigned((ntiles + 255) / 256), 256, 0, stream, ntiles,
-              reinterpret_cast<u32*>(d_payload), out_word_cap, ws);
-    rc = check_launch();
-  }
-  return rc;
+int encode_with_device_code(const uint8_t* d_in, uint64_t n, const gh_device_code* d_code, uint8_t* d_image,
+                            uint64_t image_cap, uint64_t* d_end_bit, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!d_code || !d_image || !d_workspace || !d_in) return GH_ERR_ARG;
+  if (n == 0) return GH_ERR_EMPTY;
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_image) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_workspace) & 7))
+    return GH_ERR_ARG;
+  if (workspace_bytes < enc_ws_bytes(n)) return GH_ERR_SPACE;
+  return encode_launch(d_in, n, &d_code->table, d_code, 0, 1, d_image, image_cap / 4 * 4, reinterpret_cast<u64*>(d_end_bit),
+                       static_cast<uint8_t*>(d_workspace) + kEncTableSlot, stream);
 }
 
 }  // namespace gh

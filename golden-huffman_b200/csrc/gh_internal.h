@@ -50,10 +50,7 @@ struct DecodeTables {
 int build_decode_tables(const gh_code* code, DecodeTables* t);
 
 // ---- encode table: (codeword, length) per byte + the end mark, passed to kernels by value -----------
-struct EncodeTable {
-  uint32_t codeword[GH_NSYM];
-  uint8_t length[GH_NSYM + 3];
-};
+typedef gh_encode_table EncodeTable;  // include/gh_codec.h: also a member of gh_device_code
 int build_encode_table(const gh_code* code, EncodeTable* t);
 
 // gh_decode with a non-zero first-codeword position (the payload of a .crs2 image starts 8-byte aligned, the
@@ -66,6 +63,12 @@ int decode_full(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code*
 int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint64_t start_bit, int append_eof,
                      uint8_t* d_payload, uint64_t payload_cap, uint64_t* d_end_bit, void* d_workspace,
                      size_t workspace_bytes, void* stream);
+
+// gh_compress_device with the code built on the device: packs d_in behind the header that build_code_kernel wrote to
+// the front of d_image (the payload's place follows from d_code->header_bytes, read by the kernel), bounded by
+// image_cap bytes. *d_end_bit receives the payload's end bit, counted from the 32-byte boundary below the header's end.
+int encode_with_device_code(const uint8_t* d_in, uint64_t n, const gh_device_code* d_code, uint8_t* d_image,
+                            uint64_t image_cap, uint64_t* d_end_bit, void* d_workspace, size_t workspace_bytes, void* stream);
 
 }  // namespace gh
 #endif

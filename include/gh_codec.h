@@ -56,6 +56,23 @@ typedef struct gh_code {
   uint32_t first_code[33]; /* first_code_[1..max_len]; 1024 sentinel below min_len */
 } gh_code;
 
+/* The kernels' lookup form of the encoder's tables: (codeword, length) per symbol, lengths as bytes. */
+typedef struct gh_encode_table {
+  uint32_t codeword[GH_NSYM];
+  uint8_t length[GH_NSYM + 3];
+} gh_encode_table;
+
+/* What gh_build_code_device leaves in DEVICE memory: the code, its status and sizes, and the encode table. */
+typedef struct gh_device_code {
+  gh_code code;
+  uint32_t status;        /* GH_OK, GH_ERR_EMPTY (all counters zero) or GH_ERR_TOO_LONG (a length > 32) */
+  uint32_t header_bytes;  /* 1040 + 8 * max_len */
+  uint32_t reserved;      /* keeps the 64-bit fields 8-byte aligned without implicit padding */
+  uint64_t payload_bits;  /* sum of length * count + the end mark; the 1-padding is not included */
+  uint64_t total_symbols; /* sum of the byte counters */
+  gh_encode_table table;
+} gh_device_code;
+
 const char* gh_strerror(int status);
 /* cudaError_t of the last failing CUDA call made by this library on the calling thread (0 = none) */
 int gh_last_cuda_error(void);
@@ -83,6 +100,14 @@ void gh_debug_disable_phase_walk(int off);
  * ::do_gen_encode (:69-141). Ties are broken exactly as the reference's
  * std::priority_queue<int, std::deque<int>, HuffNodeIndexGreater> does (include/canonical_huff_encoder.h:58-70). */
 int gh_build_code(const uint64_t hist256[256], gh_code* code);
+
+/* The same construction ON THE DEVICE, by one warp: bit-for-bit gh_build_code's result for
+ * the sum of the n_hists histograms at d_hists (n_hists * 256 counters, device memory; n_hists > 1 = the shards of
+ * one input), left in *d_code (device memory). d_header, when not NULL, receives the header's bytes (device memory,
+ * 4-byte aligned, >= 1296 bytes): write_encode_info (include/canonical_huff_encoder.cc:210-242) without the host.
+ * Nothing is synchronised: the result is consumed by later work on the same stream (gh_compress_device does so when
+ * gh_ctx_set_device_code is on). */
+int gh_build_code_device(const uint64_t* d_hists, int n_hists, gh_device_code* d_code, uint8_t* d_header, void* stream);
 
 /* Header size = 1040 + 8*max_len. Replaces CanonicalHuffEncoder::write_encode_info
  * (include/canonical_huff_encoder.cc:210-242). */
@@ -164,6 +189,10 @@ int gh_ctx_create(gh_ctx** ctx);
 void gh_ctx_destroy(gh_ctx* ctx);
 /* run the context's work on the caller's stream (e.g. the framework's current stream) instead of its own */
 int gh_ctx_set_stream(gh_ctx* ctx, void* stream);
+/* on != 0: gh_compress_device / gh_compress_host build the code on the device (gh_build_code_device) and run
+ * histogram -> code -> header -> packing back to back on the stream, with ONE read-back at the end; 0 (default):
+ * the histogram is read back and the code is built on the host (gh_build_code). Same image either way. */
+int gh_ctx_set_device_code(gh_ctx* ctx, int on);
 
 uint64_t gh_compress_bound(uint64_t n); /* 1040 + 8*32 + 4*n + 32 */
 int gh_compress_host(gh_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes);

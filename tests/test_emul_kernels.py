@@ -338,3 +338,88 @@ def test_emulated_forced_pipelines(emu, ctx, oracle, mode):
     finally:
         emu.lib.gh_debug_select_writer(0)
         emu.lib.gh_debug_disable_phase_walk(0)
+
+
+def _random_histograms(rng, count):
+    """histograms of many shapes: flat (every tie goes through the heap's order), geometric, Fibonacci (lengths up to
+    32 and beyond), sparse, single-valued"""
+    out = []
+    for i in range(count):
+        kind = i % 6
+        k = int(rng.integers(1, 257))
+        h = np.zeros(256, dtype=np.uint64)
+        idx = rng.permutation(256)[:k]
+        if kind == 0:
+            h[idx] = rng.integers(1, 4, k)                 # heavy ties
+        elif kind == 1:
+            h[idx] = rng.integers(1, 1 << 20, k)
+        elif kind == 2:
+            h[idx] = (rng.geometric(0.02, k)).astype(np.uint64)
+        elif kind == 3:
+            f = [1, 2]
+            while len(f) < k:
+                f.append(f[-1] + f[-2])
+            h[idx] = np.array(f[:k], dtype=np.float64).clip(max=2 ** 62).astype(np.uint64)  # long codes; may exceed 32
+        elif kind == 4:
+            h[idx] = int(rng.integers(1, 1000))            # all equal
+        else:
+            h[idx] = rng.integers(0, 3, k)                 # zeros among them
+        out.append(h)
+    return out
+
+
+def _check_device_build(lib, hists, device_alloc, to_host):
+    """gh_build_code_device == gh_build_code field by field, header and payload size included"""
+    import golden_huffman_b200 as gh
+    from golden_huffman_b200.capi import GhError
+    for h in hists:
+        d_h, d_code, d_hdr = device_alloc(h)
+        lib.build_code_device(d_h, 1, d_code, d_hdr)
+        got = gh.GhDeviceCode.from_buffer_copy(to_host(d_code, C.sizeof(gh.GhDeviceCode)))
+        try:
+            want = lib.build_code(h)
+            rc = 0
+        except GhError as e:
+            rc = e.status
+        assert got.status == rc, (got.status, rc)
+        if rc != 0:
+            continue
+        assert bytes(got.code) == bytes(want)
+        hdr = lib.write_header(want)
+        assert got.header_bytes == len(hdr) and to_host(d_hdr, len(hdr)) == hdr
+        assert got.payload_bits == lib.payload_bits(want, h, with_eof=True)
+        assert got.total_symbols == int(h.sum())
+        assert list(got.table.codeword) == list(want.codeword) and list(got.table.length)[:257] == list(want.length)
+
+
+def test_emulated_device_code_builder(emu):
+    """the one-warp code builder (csrc/gh_build.cu) against the host builder: 300 histograms of every shape"""
+    import golden_huffman_b200 as gh
+    rng = np.random.default_rng(41)
+    keep = []
+
+    def alloc(h):
+        d_h = aligned(256, np.uint64)
+        d_h[:] = h
+        d_code = aligned(C.sizeof(gh.GhDeviceCode) + 64)
+        d_hdr = aligned(2048)
+        keep[:] = [d_h, d_code, d_hdr]
+        return d_h.ctypes.data, d_code.ctypes.data, d_hdr.ctypes.data
+
+    def to_host(ptr, n):
+        return C.string_at(ptr, n)
+
+    _check_device_build(emu, _random_histograms(rng, 300), alloc, to_host)
+
+
+def test_emulated_compress_with_device_code(emu, oracle):
+    """gh_compress_device with the code built on the device: the oracle's image"""
+    c = emu.ctx_create()
+    emu.ctx_set_device_code(c, True)
+    try:
+        rng = np.random.default_rng(5)
+        for data in (make_input("kat1_abracadabra"), make_input("text_small"), make_input("kat3_allbytes512"),
+                     np.minimum(rng.geometric(0.2, 50001), 255).astype(np.uint8).tobytes(), b"x"):
+            _roundtrip(emu, c, oracle, data)
+    finally:
+        emu.ctx_destroy(c)

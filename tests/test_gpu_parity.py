@@ -353,3 +353,54 @@ def test_decode_payload_alignment(codec, oracle, name, shift):
     buf[off:off + nbytes].copy_(payload[:nbytes])
     out, n, rc = codec.decode(buf[off:off + nbytes], nbytes, code, len(data))
     assert rc == 0 and n == len(data) and _bytes(out[:n]) == data
+
+
+@pytest.mark.gpu
+def test_device_code_builder_matches_host(codec):
+    """build_code_kernel (one warp) == gh_build_code on 400 histograms of every shape (ties, long codes, lengths beyond
+    32 rejected the same way), header bytes and payload size included"""
+    import ctypes as C
+    import torch
+    import golden_huffman_b200 as gh
+    from test_emul_kernels import _random_histograms, _check_device_build
+    rng = np.random.default_rng(77)
+    keep = []
+
+    def alloc(h):
+        d_h = torch.from_numpy(h.astype(np.int64)).cuda()
+        d_code = torch.zeros(C.sizeof(gh.GhDeviceCode) + 64, dtype=torch.uint8, device="cuda")
+        d_hdr = torch.zeros(2048, dtype=torch.uint8, device="cuda")
+        keep[:] = [d_h, d_code, d_hdr]
+        return d_h.data_ptr(), d_code.data_ptr(), d_hdr.data_ptr()
+
+    def to_host(ptr, n):
+        torch.cuda.synchronize()
+        for t in keep:
+            if t.data_ptr() == ptr:
+                return t.view(torch.uint8)[:n].cpu().numpy().tobytes()
+        raise AssertionError("unknown device pointer")
+
+    _check_device_build(codec.lib, _random_histograms(rng, 400), alloc, to_host)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["zipf", "uniform", "text", "skewed"])
+def test_compress_with_device_code(codec, oracle, name):
+    """gh_compress_device with gh_ctx_set_device_code on (histogram -> code -> header -> packing without the host):
+    the image the host-code path produces, which is the oracle's"""
+    import torch
+    import golden_huffman_b200.workloads as w
+    n = (1 << 24) + 1234 if name != "skewed" else (1 << 25)
+    x = w.WORKLOADS_TORCH[name](n, "cuda", seed=9)
+    ref = codec.compress(x).clone()
+    codec.lib.ctx_set_device_code(codec.ctx, True)
+    try:
+        img = codec.compress(x)
+        assert img.numel() == ref.numel() and torch.equal(img, ref)
+        out, nd, rc = codec.decompress(img, n)
+        assert rc == 0 and nd == n and torch.equal(out, x)
+    finally:
+        codec.lib.ctx_set_device_code(codec.ctx, False)
+    rc, oimg = oracle.compress(x[: 1 << 22].cpu().numpy().tobytes())
+    small = codec.compress(x[: 1 << 22].clone())
+    assert rc == 0 and small.cpu().numpy().tobytes() == oimg

@@ -34,6 +34,8 @@
 // stage_slow). A Huffman code gives such lengths only to symbols rarer than 2^-16 or so. A tile whose bits do not fit
 // one staging buffer (more than ~12 bits per byte on average) drains the group's pipeline, is staged across all three
 // buffers and copied out at once (the "big tile" path).
+#include <string.h>
+
 #include "gh_common.cuh"
 
 namespace gh {
@@ -292,12 +294,15 @@ __device__ __forceinline__ void enc_clear(u32* buf, u32 tile_bits, u32 t) {
   for (u32 i = t; i < (tile_bits >> 7) + 1u; i += kEncGroupThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// kDeviceCode = false: the encode table arrives by value (constant bank), built on the host; true: the code was built on
+// the device, table and placement are read from *dyn.
+template <bool kDeviceCode>
 __global__ void __launch_bounds__(kEncThreads, 1)
-encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable* __restrict__ tablep, const gh_device_code* __restrict__ dyn,
+encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable table_val, const gh_device_code* __restrict__ dyn,
               u64 start_bit, int append_eof, u32* __restrict__ out_words, u64 out_word_cap, u64* __restrict__ end_bit_out,
               EncWorkspace ws, u32 smem_bytes) {
   GH_DYNAMIC_SMEM(smem_raw);
-  if (dyn) {
+  if (kDeviceCode) {
     // the code was built on the device: the payload follows the header build_code_kernel wrote, and is packed from the
     // 32-byte boundary below the header's end on (the decoder reads whole 32-byte sectors from there)
     if (dyn->status != u32(GH_OK)) return;
@@ -306,7 +311,7 @@ encode_kernel(const uint8_t* __restrict__ in, u64 n, const EncodeTable* __restri
     out_word_cap = out_word_cap > base / 4 ? out_word_cap - base / 4 : 0;
     start_bit = u64(hdr - base) * 8;
   }
-  const EncodeTable& table = *tablep;
+  const EncodeTable& table = kDeviceCode ? dyn->table : table_val;
   const unsigned group = threadIdx.x / kEncGroupThreads, tg = threadIdx.x % kEncGroupThreads;
   const unsigned lane = tg & 31, wg = tg >> 5;
 
@@ -547,10 +552,9 @@ encode_stitch_kernel(u64 ntiles, const gh_device_code* __restrict__ dyn, u32* __
   if (word < out_word_cap) out_words[word] |= be32(bits);
 }
 
-constexpr size_t kEncTableSlot = 2048;  // the encode table, in front of the workspace, when it comes from the host
 inline size_t enc_ws_bytes(u64 n) {
   const u64 nt = enc_num_tiles(n) + 1;
-  return kEncTableSlot + size_t(nt * 8 + ((nt * 4 + 7) / 8) * 8 + 256);
+  return size_t(nt * 8 + ((nt * 4 + 7) / 8) * 8 + 256);
 }
 
 }  // namespace gh
@@ -577,9 +581,9 @@ int gh_encode(const uint8_t* d_in, uint64_t n, const gh_code* code, uint64_t sta
 
 namespace gh {
 
-// the launches shared by both entry points: the table is at d_table (device), `dyn` tells the kernels to place the
-// payload behind a device-written header
-static int encode_launch(const uint8_t* d_in, u64 n, const EncodeTable* d_table, const gh_device_code* dyn, u64 start_bit,
+// the launches shared by both entry points: `table` by value (host-built code) or `dyn` (device-built code: table and
+// placement of the payload behind the device-written header come from *dyn)
+static int encode_launch(const uint8_t* d_in, u64 n, const EncodeTable& table, const gh_device_code* dyn, u64 start_bit,
                          int append_eof, uint8_t* d_payload, u64 payload_cap, u64* d_end_bit, uint8_t* ws_bytes_ptr, void* stream) {
   const u64 ntiles = enc_num_tiles(n);
   if (ntiles > 0x7ffffff0ull) return GH_ERR_ARG;
@@ -597,14 +601,20 @@ static int encode_launch(const uint8_t* d_in, u64 n, const EncodeTable* d_table,
   int dev = 0, smem_max = 0;
   GH_CUDA_TRY(cudaGetDevice(&dev));
   GH_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   const u64 out_word_cap = payload_cap / 4;
   // persistent: one CTA per SM, four tile-taking groups each
   u64 blocks = u64(sm_count() > 0 ? sm_count() : 1);
   const u64 want = (ntiles + kEncGroups - 1) / kEncGroups;
   if (blocks > want) blocks = want;
-  GH_LAUNCH(encode_kernel, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, d_table, dyn, (u64)start_bit,
-            append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, d_end_bit, ws, u32(smem_max));
+  if (dyn) {
+    GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    GH_LAUNCH(encode_kernel<true>, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, dyn, (u64)start_bit,
+              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, d_end_bit, ws, u32(smem_max));
+  } else {
+    GH_CUDA_TRY(cudaFuncSetAttribute(encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    GH_LAUNCH(encode_kernel<false>, unsigned(blocks), kEncThreads, size_t(smem_max), stream, d_in, (u64)n, table, dyn, (u64)start_bit,
+              append_eof, reinterpret_cast<u32*>(d_payload), out_word_cap, d_end_bit, ws, u32(smem_max));
+  }
   int rc = check_launch();
   if (rc != GH_OK) return rc;
   if (ntiles > 1) {
@@ -628,11 +638,8 @@ int encode_unchecked(const uint8_t* d_in, uint64_t n, const gh_code* code, uint6
   EncodeTable table;
   int rc = build_encode_table(code, &table);
   if (rc != GH_OK) return rc;
-  // the table travels to the front of the workspace (pageable source: the copy is staged before this call returns)
-  uint8_t* const w = static_cast<uint8_t*>(d_workspace);
-  GH_CUDA_TRY(cudaMemcpyAsync(w, &table, sizeof(table), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  return encode_launch(d_in, n, reinterpret_cast<const EncodeTable*>(w), nullptr, start_bit, append_eof, d_payload, payload_cap,
-                       reinterpret_cast<u64*>(d_end_bit), w + kEncTableSlot, stream);
+  return encode_launch(d_in, n, table, nullptr, start_bit, append_eof, d_payload, payload_cap, reinterpret_cast<u64*>(d_end_bit),
+                       static_cast<uint8_t*>(d_workspace), stream);
 }
 
 int encode_with_device_code(const uint8_t* d_in, uint64_t n, const gh_device_code* d_code, uint8_t* d_image,
@@ -643,8 +650,10 @@ int encode_with_device_code(const uint8_t* d_in, uint64_t n, const gh_device_cod
       (reinterpret_cast<uintptr_t>(d_workspace) & 7))
     return GH_ERR_ARG;
   if (workspace_bytes < enc_ws_bytes(n)) return GH_ERR_SPACE;
-  return encode_launch(d_in, n, &d_code->table, d_code, 0, 1, d_image, image_cap / 4 * 4, reinterpret_cast<u64*>(d_end_bit),
-                       static_cast<uint8_t*>(d_workspace) + kEncTableSlot, stream);
+  EncodeTable unused;
+  memset(&unused, 0, sizeof(unused));
+  return encode_launch(d_in, n, unused, d_code, 0, 1, d_image, image_cap / 4 * 4, reinterpret_cast<u64*>(d_end_bit),
+                       static_cast<uint8_t*>(d_workspace), stream);
 }
 
 }  // namespace gh

@@ -94,6 +94,11 @@ SIGNATURES = {
     "gh_decompress_host": (_INT, [_VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
     "gh_compress_device": (_INT, [_VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
     "gh_decompress_device": (_INT, [_VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
+    "gh_stream_create": (_INT, [C.POINTER(_VP), _U64, _U64]),
+    "gh_stream_destroy": (None, [_VP]),
+    "gh_stream_histogram": (_INT, [_VP, _VP, _VP]),
+    "gh_stream_encode": (_INT, [_VP, _VP, _VP, _CODEP, C.POINTER(_U64)]),
+    "gh_stream_decode": (_INT, [_VP, _VP, _VP, _CODEP, _U64, C.POINTER(_U64)]),
     "gh_stage_input": (_INT, [_VP, _VP, _U64, _VP]),
     "gh_encode_staged": (_INT, [_VP, _CODEP, _VP, _U64, C.POINTER(_U64)]),
     "gh_stage_payload": (_INT, [_VP, _VP, _U64, _CODEP, C.POINTER(_U64)]),

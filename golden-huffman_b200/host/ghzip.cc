@@ -1,4 +1,4 @@
-// ghzip <infile> <type> [outfile]
+// ghzip <infile> <type> [outfile] [chunk_bytes [resident_max_bytes]]
 // Same command shape as the reference's test driver (reference unit_tests/test.cc:291-317):
 //   type 3 = canonical compress (<infile>.crs2), 4/5/6 = canonical decompress (<infile>.de) -- the three
 //   reference decoders produce identical output, so all three map to the one GPU decoder.
@@ -26,6 +26,8 @@ int main(int argc, char** argv) {
   const std::string in(argv[1]);
   std::string out(argc > 3 ? argv[3] : "");
   const int type = atoi(argv[2]);
+  // optional streaming geometry (tests: small chunks, nothing resident -> the multi-pass path on a small file)
+  if (argc > 4) glzip_b200::GpuStream::set_geometry(strtoull(argv[4], NULL, 10), argc > 5 ? strtoull(argv[5], NULL, 10) : ~0ull);
   try {
     if (type == 3) {
       frame::Compressor<glzip_b200::GpuCanonicalHuffEncoder> compressor;

@@ -13,8 +13,10 @@
 // the template contract returns void, so these adapters throw std::runtime_error on any non-zero C-ABI status
 // (empty input, code length > 32, malformed stream, no CUDA device: there is no CPU fallback).
 //
-// Every per-byte operation happens on the GPU through the C ABI (include/gh_codec.h); this file only moves
-// whole files between disk and pinned-free host buffers. Header-only, depends on gh_codec.h and libgh_b200.so.
+// Every per-byte operation happens on the GPU through the C ABI (include/gh_codec.h). Files are STREAMED, as the
+// reference streams them through its 64 KiB buffers (include/encoder.h:55,136-150): chunks of 64 MiB through two
+// pinned host buffers (gh_stream_*), so a file of any size needs a fixed amount of host and device memory, and the
+// disk, the PCIe link and the kernels overlap. Header-only, depends on gh_codec.h and libgh_b200.so.
 #ifndef GPU_CANONICAL_HUFF_H_
 #define GPU_CANONICAL_HUFF_H_
 
@@ -22,7 +24,6 @@
 
 #include <stdexcept>
 #include <string>
-#include <vector>
 
 #include "gh_codec.h"
 
@@ -32,33 +33,35 @@ inline void gh_check(int status, const char* what) {
   if (status != GH_OK) throw std::runtime_error(std::string(what) + ": " + gh_strerror(status));
 }
 
-class GpuContext {  // one per encoder/decoder object; owns the device scratch buffers
+class GpuStream {  // one per encoder/decoder object; owns the pinned and device chunk buffers
  public:
-  GpuContext() : ctx_(NULL) {}
-  ~GpuContext() { reset(); }
-  gh_ctx* get() {
-    if (!ctx_) gh_check(gh_ctx_create(&ctx_), "gh_ctx_create");
-    return ctx_;
+  GpuStream() : s_(NULL) {}
+  ~GpuStream() { reset(); }
+  gh_stream* get() {
+    // chunk size and resident limit: the library's defaults (64 MiB; a quarter of the free device memory), or the
+    // values a test set through set_geometry()
+    if (!s_) gh_check(gh_stream_create(&s_, chunk_bytes(), resident_max()), "gh_stream_create");
+    return s_;
   }
   void reset() {
-    if (ctx_) gh_ctx_destroy(ctx_);
-    ctx_ = NULL;
+    if (s_) gh_stream_destroy(s_);
+    s_ = NULL;
   }
+  static uint64_t& chunk_bytes() {
+    static uint64_t v = 0;
+    return v;
+  }
+  static uint64_t& resident_max() {
+    static uint64_t v = ~0ull;
+    return v;
+  }
+  static void set_geometry(uint64_t chunk, uint64_t resident) { chunk_bytes() = chunk, resident_max() = resident; }
 
  private:
-  GpuContext(const GpuContext&);
-  GpuContext& operator=(const GpuContext&);
-  gh_ctx* ctx_;
+  GpuStream(const GpuStream&);
+  GpuStream& operator=(const GpuStream&);
+  gh_stream* s_;
 };
-
-inline bool read_whole_file(FILE* f, std::vector<unsigned char>& buf) {
-  if (!f) return false;
-  if (fseek(f, 0, SEEK_END) != 0) return false;
-  long size = ftell(f);
-  if (size < 0 || fseek(f, 0, SEEK_SET) != 0) return false;
-  buf.resize(size_t(size));
-  return size == 0 || fread(&buf[0], 1, size_t(size), f) == size_t(size);
-}
 
 class GpuCanonicalHuffEncoder {
  public:
@@ -83,10 +86,10 @@ class GpuCanonicalHuffEncoder {
     infile_ = outfile_ = NULL;
   }
 
-  // step 1 of Compressor::compress(): whole file -> device, K1 histogram (reference encoder.h:136-150)
+  // step 1 of Compressor::compress(): pass 1 over the file, chunk by chunk -> K1 (reference encoder.h:136-150)
   void caculate_frequency() {
-    if (!read_whole_file(infile_, input_)) throw std::runtime_error("GpuCanonicalHuffEncoder: read failed: " + infile_name_);
-    gh_check(gh_stage_input(gpu_.get(), input_.empty() ? NULL : &input_[0], input_.size(), hist_), "gh_stage_input");
+    fseek(infile_, 0, SEEK_SET);
+    gh_check(gh_stream_histogram(gpu_.get(), infile_, hist_), "gh_stream_histogram");
   }
 
   // step 2: code lengths + canonical codewords, reference tie-breaking (canonical_huff_encoder.cc:35-42)
@@ -105,13 +108,10 @@ class GpuCanonicalHuffEncoder {
   // step 4: payload, end mark and 1-padding (canonical_huff_encoder.cc:245-285)
   void encode_file() {
     const uint64_t bytes = (gh_payload_bits(&code_, hist_, 1) + 7) / 8;
-    std::vector<unsigned char> payload(bytes + 16);
     uint64_t got = 0;
-    gh_check(gh_encode_staged(gpu_.get(), &code_, &payload[0], payload.size(), &got), "gh_encode_staged");
+    fseek(infile_, 0, SEEK_SET);
+    gh_check(gh_stream_encode(gpu_.get(), infile_, outfile_, &code_, &got), "gh_stream_encode");
     if (got != bytes) throw std::runtime_error("GpuCanonicalHuffEncoder: payload size mismatch");
-    if (fwrite(&payload[0], 1, got, outfile_) != got) throw std::runtime_error("GpuCanonicalHuffEncoder: payload write failed");
-    fflush(outfile_);
-    std::vector<unsigned char>().swap(input_);
   }
 
   const gh_code& code() const { return code_; }
@@ -122,10 +122,9 @@ class GpuCanonicalHuffEncoder {
   FILE* infile_;
   FILE* outfile_;
   std::string infile_name_;
-  std::vector<unsigned char> input_;
   uint64_t hist_[256];
   gh_code code_;
-  GpuContext gpu_;
+  GpuStream gpu_;
 };
 
 class GpuCanonicalHuffDecoder {
@@ -143,19 +142,17 @@ class GpuCanonicalHuffDecoder {
 
   // step 1 of Decompressor::decompress(): header -> tables (canonical_huff_encoder.cc:349-374)
   void get_encode_info() {
-    if (!read_whole_file(infile_, image_)) throw std::runtime_error("GpuCanonicalHuffDecoder: read failed");
-    gh_check(gh_parse_header(image_.empty() ? NULL : &image_[0], image_.size(), &code_, &header_bytes_), "gh_parse_header");
+    unsigned char hdr[1040 + 8 * 32];
+    fseek(infile_, 0, SEEK_SET);
+    const size_t got = fread(hdr, 1, sizeof(hdr), infile_);
+    gh_check(gh_parse_header(hdr, got, &code_, &header_bytes_), "gh_parse_header");
   }
 
   // step 2: decode up to the end mark (canonical_huff_encoder.cc:377-419)
   void decode_file() {
-    if (image_.size() <= header_bytes_) throw std::runtime_error("GpuCanonicalHuffDecoder: no payload");
     uint64_t n = 0;
-    gh_check(gh_stage_payload(gpu_.get(), &image_[header_bytes_], image_.size() - header_bytes_, &code_, &n), "gh_stage_payload");
-    std::vector<unsigned char> out(n ? n : 1);
-    gh_check(gh_decode_staged(gpu_.get(), &out[0], n), "gh_decode_staged");
-    if (n && fwrite(&out[0], 1, n, outfile_) != n) throw std::runtime_error("GpuCanonicalHuffDecoder: write failed");
-    fflush(outfile_);
+    if (fseek(infile_, long(header_bytes_), SEEK_SET) != 0) throw std::runtime_error("GpuCanonicalHuffDecoder: seek failed");
+    gh_check(gh_stream_decode(gpu_.get(), infile_, outfile_, &code_, header_bytes_, &n), "gh_stream_decode");
   }
 
  private:
@@ -163,10 +160,9 @@ class GpuCanonicalHuffDecoder {
   GpuCanonicalHuffDecoder& operator=(const GpuCanonicalHuffDecoder&);
   FILE* infile_;
   FILE* outfile_;
-  std::vector<unsigned char> image_;
   size_t header_bytes_;
   gh_code code_;
-  GpuContext gpu_;
+  GpuStream gpu_;
 };
 
 }  // namespace glzip_b200

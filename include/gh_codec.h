@@ -24,6 +24,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -203,6 +204,24 @@ int gh_compress_device(gh_ctx* ctx, const uint8_t* d_in, uint64_t n, uint8_t* d_
                        uint64_t* out_bytes);
 int gh_decompress_device(gh_ctx* ctx, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
                          uint64_t* out_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Streaming files of any size through a fixed amount of memory: what the reference does with its 64 KiB
+ * FixedFileBuffer (include/encoder.h:55,136-150; include/canonical_huff_encoder.cc:245-285, 377-419), with chunks of
+ * `chunk_bytes` (0 = 64 MiB) through two pinned host buffers: the file I/O, the PCIe copies and the kernels overlap.
+ * Inputs up to `resident_max_bytes` (~0 = a quarter of the free device memory) stay on the device between the two
+ * passes of compress; larger ones are read twice, like the reference reads its input twice.
+ *   compress   = gh_stream_histogram (pass 1) -> gh_build_code -> gh_write_header -> gh_stream_encode (pass 2)
+ *   decompress = gh_parse_header -> gh_stream_decode
+ * FILE* positions: histogram reads from the current position to the end and seeks back; encode reads the same range
+ * and appends the payload to `out`; decode expects `in` at the first payload byte (header_bytes into the file).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gh_stream gh_stream;
+int gh_stream_create(gh_stream** s, uint64_t chunk_bytes, uint64_t resident_max_bytes);
+void gh_stream_destroy(gh_stream* s);
+int gh_stream_histogram(gh_stream* s, FILE* in, uint64_t hist256[256]);
+int gh_stream_encode(gh_stream* s, FILE* in, FILE* out, const gh_code* code, uint64_t* payload_bytes);
+int gh_stream_decode(gh_stream* s, FILE* in, FILE* out, const gh_code* code, uint64_t header_bytes, uint64_t* n_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Staged variants, one per step of the reference's template methods, for adapters that must keep the

@@ -66,3 +66,62 @@ def test_cli_rejects_empty_input(tmp_path, codec):
     src.write_bytes(b"")
     r = subprocess.run([cli, str(src), "3"], capture_output=True, text=True)
     assert r.returncode == 1 and "empty input" in r.stderr
+
+
+def test_streaming_small_chunks_through_cli(tmp_path, codec):
+    """the adapters stream: with 1 MiB chunks and nothing resident a 40 MB file takes the multi-pass path (file read
+    twice, 40 chunks whose payloads meet inside bytes); the .crs2 is the oracle's and decodes back, chunk by chunk"""
+    import golden_huffman_b200.workloads as w
+    from oracle_lib import Oracle
+    cli = os.path.join(LIBDIR, "ghzip")
+    data = w.zipf_np((40 << 20) + 4321, seed=31).tobytes()
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    subprocess.run([cli, str(src), "3", str(tmp_path / "s.crs2"), str(1 << 20), "0"], check=True)
+    rc, want = Oracle().compress(data)
+    assert rc == 0 and (tmp_path / "s.crs2").read_bytes() == want
+    subprocess.run([cli, str(tmp_path / "s.crs2"), "4", str(tmp_path / "s.de"), str(1 << 20), "0"], check=True)
+    assert (tmp_path / "s.de").read_bytes() == data
+    # default geometry (64 MiB chunks, resident): same bytes
+    subprocess.run([cli, str(src), "3", str(tmp_path / "d.crs2")], check=True)
+    assert (tmp_path / "d.crs2").read_bytes() == want
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="compiled reference not shipped")
+def test_file_beyond_4gib_matches_reference_binary(codec):
+    """a 4.5 GiB file through the CLI built against the reference's unmodified compressor.h, streamed in 64 MiB chunks:
+    the .crs2 is byte-identical to the one the compiled reference writes, and decodes back to the input"""
+    import hashlib
+    import tempfile
+    import golden_huffman_b200.workloads as w
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    if shutil.disk_usage(base).free < (22 << 30):
+        pytest.skip("needs ~22 GB of scratch space")
+    cli = os.path.join(LIBDIR, "ghzip_refframe")
+    if not os.path.exists(cli):
+        cli = os.path.join(LIBDIR, "ghzip")
+    d = tempfile.mkdtemp(prefix="gh_big_", dir=base)
+    try:
+        n = (9 << 29) + 777
+        src = os.path.join(d, "big.bin")
+        with open(src, "wb") as f:
+            for a in range(0, n, 1 << 30):
+                m = min(1 << 30, n - a)
+                f.write(w.text_torch(m, "cuda", seed=100 + (a >> 30)).cpu().numpy().tobytes())
+        subprocess.run([cli, src, "3", os.path.join(d, "gpu.crs2")], check=True)
+        subprocess.run([REF_BIN, src, "3", os.path.join(d, "ref.crs2")], check=True)
+
+        def sha(path):
+            h = hashlib.sha256()
+            with open(path, "rb") as f:
+                for blk in iter(lambda: f.read(1 << 24), b""):
+                    h.update(blk)
+            return h.hexdigest()
+
+        assert os.path.getsize(os.path.join(d, "gpu.crs2")) == os.path.getsize(os.path.join(d, "ref.crs2"))
+        assert sha(os.path.join(d, "gpu.crs2")) == sha(os.path.join(d, "ref.crs2"))
+        os.unlink(os.path.join(d, "ref.crs2"))
+        subprocess.run([cli, os.path.join(d, "gpu.crs2"), "4", os.path.join(d, "gpu.de")], check=True)
+        assert os.path.getsize(os.path.join(d, "gpu.de")) == n and sha(os.path.join(d, "gpu.de")) == sha(src)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

@@ -23,7 +23,7 @@
 //      of the iteration then frees that buffer (cleared; re-used by tile k+1).
 //      A tile's count is thus published a whole tile period before anybody asks for it, and nobody waits for a
 //      look-back. With look-back and copy-out right after staging, the groups ran in lock step with the slowest SM:
-//      38-47 % of the warp samples sat at the barrier behind the look-back (profiles/r2_enc_notes.md).
+//      38-47 % of the warp samples sat at the barrier behind the look-back (profiles/rnd2_notes.md).
 //      The tile's first word, when shared with the previous tile, is NOT stored: its bits go to head[tile] and
 //      encode_stitch_kernel ORs them into the word the previous tile wrote -- every output word has exactly one
 //      writer per kernel, no global atomics on the payload. The last tile adds the 1-padding (reference

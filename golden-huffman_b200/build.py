@@ -15,7 +15,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgh_b200.so")
 CLI = os.path.join(LIBDIR, "ghzip")
 
-CU_SOURCES = ["gh_runtime.cu", "gh_hist.cu", "gh_encode.cu", "gh_decode.cu", "gh_build.cu", "gh_stream.cu", "gh_api.cu"]
+CU_SOURCES = ["gh_runtime.cu", "gh_hist.cu", "gh_encode.cu", "gh_decode.cu", "gh_build.cu", "gh_stream.cu", "gh_multi.cu", "gh_api.cu"]
 CC_SOURCES = ["gh_host.cc"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

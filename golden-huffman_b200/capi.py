@@ -99,6 +99,8 @@ SIGNATURES = {
     "gh_stream_histogram": (_INT, [_VP, _VP, _VP]),
     "gh_stream_encode": (_INT, [_VP, _VP, _VP, _CODEP, C.POINTER(_U64)]),
     "gh_stream_decode": (_INT, [_VP, _VP, _VP, _CODEP, _U64, C.POINTER(_U64)]),
+    "gh_compress_host_multi": (_INT, [_INT, _VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
+    "gh_decompress_host_multi": (_INT, [_INT, _VP, _VP, _U64, _VP, _U64, C.POINTER(_U64)]),
     "gh_stage_input": (_INT, [_VP, _VP, _U64, _VP]),
     "gh_encode_staged": (_INT, [_VP, _CODEP, _VP, _U64, C.POINTER(_U64)]),
     "gh_stage_payload": (_INT, [_VP, _VP, _U64, _CODEP, C.POINTER(_U64)]),
@@ -250,6 +252,23 @@ class GhLib:
 
     def decompress_host(self, ctx, src, n, dst, cap, allow=()):
         return self._image_call(self.lib.gh_decompress_host, "gh_decompress_host", ctx, src, n, dst, cap, allow)
+
+    def compress_host_multi(self, devices, src, n, dst, cap, allow=()):
+        """devices: list of device ordinals, one per shard (a device may repeat)"""
+        arr = (C.c_int * len(devices))(*devices)
+        out = C.c_uint64(0)
+        rc = self.lib.gh_compress_host_multi(len(devices), C.cast(arr, C.c_void_p), src, n, dst, cap, C.byref(out))
+        if rc not in allow:
+            self.check(rc, "gh_compress_host_multi")
+        return int(out.value), rc
+
+    def decompress_host_multi(self, devices, src, n, dst, cap, allow=()):
+        arr = (C.c_int * len(devices))(*devices)
+        out = C.c_uint64(0)
+        rc = self.lib.gh_decompress_host_multi(len(devices), C.cast(arr, C.c_void_p), src, n, dst, cap, C.byref(out))
+        if rc not in allow:
+            self.check(rc, "gh_decompress_host_multi")
+        return int(out.value), rc
 
     def compress_device(self, ctx, src, n, dst, cap, allow=()):
         return self._image_call(self.lib.gh_compress_device, "gh_compress_device", ctx, src, n, dst, cap, allow)

@@ -199,6 +199,15 @@ uint64_t gh_compress_bound(uint64_t n); /* 1040 + 8*32 + 4*n + 32 */
 int gh_compress_host(gh_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 int gh_decompress_host(gh_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 
+/* Same on N GPUs of one box from ONE process (no NCCL: the data comes from and returns to host memory, so what the shards
+ * exchange -- 256 counters, one boundary byte, one bit position -- crosses on the host): the input is cut into n_shards
+ * contiguous shards, shard d runs on device devices[d] (NULL: device d) in its own host thread. A device may be listed
+ * more than once. Same image / same bytes as the single-GPU calls. */
+int gh_compress_host_multi(int n_shards, const int* devices, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
+                           uint64_t* out_bytes);
+int gh_decompress_host_multi(int n_shards, const int* devices, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
+                             uint64_t* out_bytes);
+
 /* Same, with device-resident input and output (no PCIe traffic): the kernels-only path bench.py times. */
 int gh_compress_device(gh_ctx* ctx, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
                        uint64_t* out_bytes);

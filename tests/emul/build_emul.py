@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "golden-huffman_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libgh_emul.so")
-CU = ["gh_runtime.cu", "gh_hist.cu", "gh_encode.cu", "gh_decode.cu", "gh_build.cu", "gh_stream.cu", "gh_api.cu"]
+CU = ["gh_runtime.cu", "gh_hist.cu", "gh_encode.cu", "gh_decode.cu", "gh_build.cu", "gh_stream.cu", "gh_multi.cu", "gh_api.cu"]
 
 
 def build(force=False, sanitize=False):

@@ -270,6 +270,7 @@ static inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *fre
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
   *v = (a == cudaDevAttrMultiProcessorCount) ? gh_emul::g_sm_count : gh_emul::kMaxDynSmem;

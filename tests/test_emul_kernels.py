@@ -471,3 +471,27 @@ def test_emulated_streaming_files(emu, oracle, tmp_path, resident):
     for data, chunk in ((make_input("text_small") * 40, 65536), (W.zipf_np(200001, seed=3).tobytes(), 12288),
                         (W.uniform_np(70000, seed=4).tobytes(), 4096), (b"abracadabra", 4096), (b"q", 4096)):
         _stream_file_roundtrip(emu, oracle, tmp_path, data, chunk, resident)
+
+
+def _multi_roundtrip(lib, oracle, data, shards):
+    n = len(data)
+    src = np.frombuffer(data, dtype=np.uint8).copy()
+    rc, want = oracle.compress(data)
+    assert rc == 0
+    img = np.zeros(lib.compress_bound(n), dtype=np.uint8)
+    nb, _ = lib.compress_host_multi(shards, src.ctypes.data, n, img.ctypes.data, img.size)
+    assert img[:nb].tobytes() == want
+    out = np.zeros(n + 8, dtype=np.uint8)
+    nd, _ = lib.decompress_host_multi(shards, img.ctypes.data, nb, out.ctypes.data, n)
+    assert nd == n and out[:n].tobytes() == data
+
+
+def test_emulated_multi_shard_host_api(emu, oracle):
+    """gh_compress_host_multi / gh_decompress_host_multi: 1, 2, 3 and 5 shards (here all on the one emulated device): the
+    shards meet inside bytes (encode) and inside codewords (decode: entries found by walking a 4 KiB left halo, checked
+    against the neighbours' exits); inputs too small for that many shards fall back to fewer"""
+    import golden_huffman_b200.workloads as W
+    for data in (make_input("text_small") * 120, W.zipf_np(150001, seed=8).tobytes(), W.uniform_np(90000, seed=9).tobytes(),
+                 make_input("kat1_abracadabra")):
+        for shards in ([0], [0, 0], [0, 0, 0], [0] * 5):
+            _multi_roundtrip(emu, oracle, data, shards)

@@ -432,3 +432,26 @@ def test_roundtrip_beyond_4gib(codec):
     step = 1 << 30
     for a in range(0, n, step):
         assert torch.equal(out[a:a + step], x[a:a + step]), f"mismatch in [{a}, {a + step})"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["zipf", "text", "uniform", "skewed"])
+def test_multi_device_host_api(codec, oracle, name):
+    """gh_compress_host_multi / gh_decompress_host_multi (one process, one host thread per shard): three shards on the
+    devices that are there (all on device 0 on a one-GPU box, which exercises the same stitching and entry logic): the
+    image is the oracle's, the output the input"""
+    import torch
+    import golden_huffman_b200.workloads as w
+    ndev = torch.cuda.device_count()
+    devices = [k % ndev for k in range(3)]
+    n = (48 << 20) + 777
+    data = w.WORKLOADS_NP[name](n, seed=17)
+    rc, want = oracle.compress(data.tobytes())
+    assert rc == 0
+    lib = codec.lib
+    img = np.zeros(lib.compress_bound(n), dtype=np.uint8)
+    nb, _ = lib.compress_host_multi(devices, data.ctypes.data, n, img.ctypes.data, img.size)
+    assert nb == len(want) and img[:nb].tobytes() == want
+    out = np.zeros(n + 8, dtype=np.uint8)
+    nd, _ = lib.decompress_host_multi(devices, img.ctypes.data, nb, out.ctypes.data, n)
+    assert nd == n and (out[:n] == data).all()

@@ -986,12 +986,12 @@ struct SmemWrite {
 
 // Output queue of the write loop, branch-free: if `word_done`, the assembled word `merged` is shifted into the
 // four-register queue and `spill` opens the next word; if `group_done`, the queue leaves as one 128-bit store to
-// the lane's 16-byte-aligned destination, which then advances. Written as predicated PTX: as C++
+// the lane's 16-byte-aligned destination (ghi:glo), which then advances. Written as predicated PTX: as C++
 // branches the compiler turns these few moves into divergent control flow that every warp then walks on almost
 // every iteration; and as predicated MOVs (not SEL) so that ptxas may place them on the FMA pipe -- the loop's
 // shifts and logic ops already fill the ALU pipe (each pipe issues a warp instruction every other cycle).
 __device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32& q3, u32& part, u32 merged, u32 spill,
-                                                 u32 word_done, u32 group_done, u32& glo, const u32 ghi, u32 one) {
+                                                 u32 word_done, u32 group_done, u32& glo, u32& ghi, u32 one) {
   (void)one;  // a register holding 1 that ptxas cannot see through: `x * one` is a move on the FMA pipe
 #ifdef GH_EMUL
   if (word_done) {
@@ -1003,13 +1003,10 @@ __device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32&
   if (group_done) {
     const u64 a = (u64(ghi) << 32) | glo;
     *reinterpret_cast<uint4*>(a) = make_uint4(q0, q1, q2, q3);
-    glo += 16;
+    glo = u32(a + 16), ghi = u32((a + 16) >> 32);
   }
 #else
   part = merged;
-  // Only the low half of the destination advances: the caller makes sure a lane's output does not cross a 4 GiB
-  // boundary (the few lanes whose output does take the slow path), so no carry, no select and no re-assembly of the
-  // address pair are needed per lookup.
   asm volatile(
       "{\n"
       " .reg .pred pw, pg;\n"
@@ -1021,12 +1018,13 @@ __device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32&
       " @pw mad.lo.u32 %2, %3, %10, 0;\n"
       " @pw mad.lo.u32 %3, %4, %10, 0;\n"
       " @pw mov.u32 %4, %7;\n"
-      " @pg add.u32 %5, %5, 16;\n"
       " mov.b64 a, {%5, %6};\n"
-      " @pg st.global.v4.u32 [a+-16], {%0, %1, %2, %3};\n"
+      " @pg st.global.v4.u32 [a], {%0, %1, %2, %3};\n"
+      " @pg add.cc.u32 %5, %5, 16;\n"
+      " @pg addc.u32 %6, %6, 0;\n"
       "}\n"
-      : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(part), "+r"(glo)
-      : "r"(ghi), "r"(spill), "r"(word_done), "r"(group_done), "r"(one)
+      : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(part), "+r"(glo), "+r"(ghi)
+      : "r"(spill), "r"(word_done), "r"(group_done), "r"(one)
       : "memory");
 #endif
 }
@@ -1094,16 +1092,13 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
     typedef CursorGeom<kLutWBits, kLutWEntryShift> G;
     u64 u, ulast;
     u32 acc;
-    const u64 dst_addr = u64(reinterpret_cast<uintptr_t>(dst));
-    const bool same_4g = (dst_addr >> 32) == ((dst_addr + remaining + 32) >> 32);  // see queue_push_store
-    if (remaining && same_4g && u64(count) <= out_cap - o && pos < end &&
+    if (remaining && u64(count) <= out_cap - o && pos < end &&
         cursor_plan<kLutWBits, kLutWEntryShift>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
       const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
       const u64 umax = (g.readable >> 5) - 1;
       const smem_addr_t lut = smem_addr(s.lutW);
-      // destination of the next 128-bit store (16-byte aligned)
-      u32 glo = u32(reinterpret_cast<uintptr_t>(dst));
-      const u32 ghi = u32(u64(reinterpret_cast<uintptr_t>(dst)) >> 32);
+      // destination of the next 128-bit store (16-byte aligned), as two words so the advance can be predicated
+      u32 glo = u32(reinterpret_cast<uintptr_t>(dst)), ghi = u32(u64(reinterpret_cast<uintptr_t>(dst)) >> 32);
       const u32 one = blockDim.x / kDecThreads;  // 1, but not to ptxas: `x * one` stays a move on the FMA pipe
       u32 q0 = 0, q1 = 0, q2 = 0, q3 = 0, part = 0;
       u32 hi, lo = 0;

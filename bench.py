@@ -158,7 +158,7 @@ def run_reference(args):
     value = n * len(times) / tot / 1e9
     enc = n * len(times) / sum(a for a, _ in times) / 1e9
     dec = n * len(times) / sum(b for _, b in times) / 1e9
-    sample = (f"the whole {args.size_mib} MiB input per step (same bytes as the GPU arm's rank 0); reference compress() + "
+    sample = (f"the whole {args.size_mib} MiB input per step (same distribution and size as one GPU's share in the GPU arm); reference compress() + "
               f"TableCanonicalHuffDecoder decompress() via files in /dev/shm; 1 thread; {host_cpu_model()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,

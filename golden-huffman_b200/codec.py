@@ -12,6 +12,20 @@ import torch
 from .capi import GhLib, GH_ERR_SPACE
 
 
+def _on_device(fn):
+    """every library call runs with the codec's device current (allocations, kernel attributes and launches are per
+    device; a process may hold codecs on several)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        if self.device.type != "cuda":  # the tests' emulated codec keeps "device" memory in CPU tensors
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class Codec:
     def __init__(self, lib=None, device=None):
         if not torch.cuda.is_available():
@@ -53,6 +67,7 @@ class Codec:
                                        "16-byte boundary (a slice such as x[1:] does not; copy it first)"
 
     # ---- the path, step by step -------------------------------------------------------------------------
+    @_on_device
     def histogram(self, x, out=None, accumulate=False):
         """K1: 256 byte counts (torch.int64 tensor on the device)."""
         self._check_u8(x)
@@ -65,6 +80,7 @@ class Codec:
         h = hist.detach().cpu().numpy().astype(np.uint64) if isinstance(hist, torch.Tensor) else np.asarray(hist, np.uint64)
         return self.lib.build_code(h)
 
+    @_on_device
     def encode(self, x, code, start_bit=0, append_eof=True, out=None):
         """K2-K4: returns (payload tensor, end_bit tensor[1] on the device)."""
         self._check_u8(x)
@@ -79,6 +95,7 @@ class Codec:
                         start_bit=start_bit, append_eof=append_eof, d_end_bit=end_bit.data_ptr(), stream=self._stream())
         return payload, end_bit
 
+    @_on_device
     def decode(self, payload, nbytes, code, out_cap, out=None, allow=()):
         """K5-K7: returns (output tensor, symbols decoded, status)."""
         self._check_u8(payload)
@@ -90,6 +107,7 @@ class Codec:
         return dst, n, rc
 
     # ---- whole .crs2 images -----------------------------------------------------------------------------
+    @_on_device
     def compress(self, x, out=None):
         """device tensor -> device .crs2 image (header + payload), kernels only."""
         self._check_u8(x)
@@ -99,6 +117,7 @@ class Codec:
         nbytes, _ = self.lib.compress_device(self.ctx, x.data_ptr(), x.numel(), img.data_ptr(), cap)
         return img[:nbytes]
 
+    @_on_device
     def decompress(self, img, out_cap, out=None, allow=()):
         self._check_u8(img)
         dst = out if out is not None else torch.empty(max(out_cap, 1), dtype=torch.uint8, device=img.device)
@@ -106,6 +125,7 @@ class Codec:
         n, rc = self.lib.decompress_device(self.ctx, img.data_ptr(), img.numel(), dst.data_ptr(), out_cap, allow=allow)
         return dst[: min(n, out_cap)], n, rc
 
+    @_on_device
     def compress_host(self, src, dst):
         """host (ideally pinned) uint8 tensors/arrays in and out; H2D + kernels + D2H inside the call."""
         sp, sn = _host_ptr(src)
@@ -113,6 +133,7 @@ class Codec:
         n, _ = self.lib.compress_host(self.ctx, sp, sn, dp, dn)
         return n
 
+    @_on_device
     def decompress_host(self, src, nbytes, dst, allow=()):
         sp, _ = _host_ptr(src)
         dp, dn = _host_ptr(dst)

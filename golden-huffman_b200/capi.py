@@ -73,6 +73,7 @@ SIGNATURES = {
     "gh_debug_disable_phase_walk": (None, [_INT]),
     "gh_ctx_set_stream": (_INT, [_VP, _VP]),
     "gh_ctx_set_device_code": (_INT, [_VP, _INT]),
+    "gh_ctx_set_host_chunk": (_INT, [_VP, _U64]),
     "gh_build_code_device": (_INT, [_VP, _INT, _VP, _VP, _VP]),
     "gh_build_code": (_INT, [_VP, _CODEP]),
     "gh_header_bytes": (_SZ, [_CODEP]),
@@ -166,6 +167,9 @@ class GhLib:
     def build_code_device(self, d_hists, n_hists, d_code, d_header=0, stream=0):
         """device pointers: n_hists x 256 u64 counters in, struct gh_device_code (and optionally the header) out"""
         self.check(self.lib.gh_build_code_device(d_hists, n_hists, d_code, d_header, stream), "gh_build_code_device")
+
+    def ctx_set_host_chunk(self, ctx, nbytes=0):
+        self.check(self.lib.gh_ctx_set_host_chunk(ctx, nbytes), "gh_ctx_set_host_chunk")
 
     def ctx_set_device_code(self, ctx, on=True):
         self.check(self.lib.gh_ctx_set_device_code(ctx, 1 if on else 0), "gh_ctx_set_device_code")

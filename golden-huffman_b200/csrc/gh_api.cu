@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "gh_common.cuh"
 
 struct gh_ctx {
@@ -19,6 +21,12 @@ struct gh_ctx {
   uint8_t* h_small;   // pinned: histogram read-back, header staging
   gh_device_code* d_code;  // code built on the device (gh_ctx_set_device_code)
   bool device_code;
+  // copy engines of the host entry points: uploads and read-backs run beside the kernels, in chunks
+  cudaStream_t copy_in, copy_out;
+  cudaEvent_t* ev_in;               // [ev_in_n] chunk k is on the device
+  size_t ev_in_n;
+  cudaEvent_t ev_dec[2];            // chunk k (mod 2) is decoded
+  uint64_t host_chunk;              // payload bytes per pipeline step of gh_decompress_host
   // state of the staged (step-by-step) entry points
   uint64_t staged_n;         // input bytes resident in d_in (gh_stage_input)
   uint64_t staged_payload;   // payload bytes resident in d_in (gh_stage_payload)
@@ -30,6 +38,37 @@ namespace gh {
 
 constexpr size_t kSmallBytes = 4096;
 constexpr size_t kMaxHeader = 1040 + 8 * 32;
+
+constexpr uint64_t kHostChunk = 64ull << 20;  // default payload bytes per pipeline step of gh_decompress_host
+constexpr size_t kMaxHostChunks = 4096;
+constexpr uint64_t kHostHalo = 64;            // bytes of the next chunk a chunk's decode may read
+
+// the side streams and `n_in` upload events, created on first use
+static int ensure_copy_engines(gh_ctx* c, size_t n_in) {
+  if (!c->copy_in) GH_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  if (!c->copy_out) GH_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i)
+    if (!c->ev_dec[i]) GH_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_dec[i], cudaEventDisableTiming));
+  if (c->ev_in_n < n_in) {
+    cudaEvent_t* grown = static_cast<cudaEvent_t*>(realloc(c->ev_in, n_in * sizeof(cudaEvent_t)));
+    if (!grown) return GH_ERR_ARG;
+    c->ev_in = grown;
+    while (c->ev_in_n < n_in) {
+      GH_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[c->ev_in_n], cudaEventDisableTiming));
+      ++c->ev_in_n;
+    }
+  }
+  return GH_OK;
+}
+
+// Nothing may still be copying from or to the caller's buffers when a host entry point returns, whatever the path out.
+struct CopyEngineFence {
+  gh_ctx* c;
+  ~CopyEngineFence() {
+    if (c->copy_in) cudaStreamSynchronize(c->copy_in);
+    if (c->copy_out) cudaStreamSynchronize(c->copy_out);
+  }
+};
 
 static int grow(void** p, size_t* cap, size_t need) {
   if (*cap >= need) return GH_OK;
@@ -64,7 +103,14 @@ int gh_ctx_create(gh_ctx** out) {
     return rc;
   }
   c->own_stream = true;
+  c->host_chunk = kHostChunk;
   *out = c;
+  return GH_OK;
+}
+
+int gh_ctx_set_host_chunk(gh_ctx* c, uint64_t bytes) {
+  if (!c) return GH_ERR_ARG;
+  c->host_chunk = bytes ? (bytes + 4095) / 4096 * 4096 : gh::kHostChunk;
   return GH_OK;
 }
 
@@ -90,6 +136,12 @@ void gh_ctx_destroy(gh_ctx* c) {
   if (c->d_small) cudaFree(c->d_small);
   if (c->d_code) cudaFree(c->d_code);
   if (c->h_small) cudaFreeHost(c->h_small);
+  for (size_t i = 0; i < c->ev_in_n; ++i) cudaEventDestroy(c->ev_in[i]);
+  free(c->ev_in);
+  for (int i = 0; i < 2; ++i)
+    if (c->ev_dec[i]) cudaEventDestroy(c->ev_dec[i]);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -208,22 +260,89 @@ int gh_compress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uin
   return GH_OK;
 }
 
+// Decompressor::decompress() from and to host memory. The payload goes up in chunks on one copy engine while the
+// chunks already there are decoded and their bytes come back on the other: a chunk's first codeword starts where
+// the previous chunk's decode ran out (gh_decode_sync's exit bit), so the chunks decode in order with nothing but
+// that bit position between them, and the call takes about as long as its larger copy (the read-back) instead of
+// upload + kernels + read-back (PCIe is full duplex).
 int gh_decompress_host(gh_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
   using namespace gh;
   if (!c || !in || !out_bytes || (!out && cap)) return GH_ERR_ARG;
+  *out_bytes = 0;
   c->staged_n = c->staged_payload = 0;  // the context's buffers are about to be reused: nothing stays staged
-  int rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, n + 16);
+  // 1. header (get_encode_info), straight from the caller's bytes
+  gh_code code;
+  size_t hdr = 0;
+  int rc = gh_parse_header(in, n < kMaxHeader ? size_t(n) : kMaxHeader, &code, &hdr);
   if (rc != GH_OK) return rc;
-  GH_CUDA_TRY(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
-  rc = grow(reinterpret_cast<void**>(&c->d_out), &c->out_cap, cap + 16);
+  if (n <= hdr) return GH_ERR_NO_EOF;
+  // 2. payload (decode_file), read from the 32-byte boundary below it (one sector per lane and request); the bytes
+  // between that boundary and the payload are skipped through chunk 0's entry bit
+  const uint64_t base = hdr & ~uint64_t(31);
+  const uint64_t stream_bytes = n - base;
+  // chunk boundaries (stream offsets, multiples of 4 KiB): the first chunks are small and double up to the configured
+  // size, so that the read-back -- the longer of the two copies -- starts after a fraction of a millisecond of upload
+  const uint64_t P = c->host_chunk;
+  uint64_t cuts[kMaxHostChunks + 1];
+  size_t nchunks = 0;
+  {
+    uint64_t at = 0, step = P / 16 >= 4096 ? (P / 16 + 4095) / 4096 * 4096 : P;
+    const uint64_t rest_chunks = (stream_bytes + P - 1) / P;
+    if (rest_chunks + 8 > kMaxHostChunks) step = (stream_bytes / (kMaxHostChunks - 8) + 4095) / 4096 * 4096;  // huge inputs: fewer, larger chunks
+    while (at < stream_bytes) {
+      cuts[nchunks++] = at;
+      at += step;
+      if (step < P) step = step * 2 < P ? step * 2 : P;
+    }
+    cuts[nchunks] = stream_bytes;
+  }
+  uint64_t largest = 0;
+  for (size_t k = 0; k < nchunks; ++k) largest = cuts[k + 1] - cuts[k] > largest ? cuts[k + 1] - cuts[k] : largest;
+  rc = grow(reinterpret_cast<void**>(&c->d_in), &c->in_cap, n + 64);
   if (rc != GH_OK) return rc;
-  uint64_t bytes = 0;
-  rc = gh_decompress_device(c, c->d_in, n, c->d_out, cap, &bytes);
-  *out_bytes = bytes;
+  rc = grow(reinterpret_cast<void**>(&c->d_out), &c->out_cap, cap + 64);
   if (rc != GH_OK) return rc;
-  GH_CUDA_TRY(cudaMemcpyAsync(out, c->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  rc = grow(&c->d_ws, &c->ws_cap, gh_decode_workspace_bytes(largest + kHostHalo));
+  if (rc != GH_OK) return rc;
+  rc = ensure_copy_engines(c, nchunks);
+  if (rc != GH_OK) return rc;
+  CopyEngineFence fence{c};
+  for (size_t k = 0; k < nchunks; ++k) {
+    const uint64_t off = base + cuts[k];
+    GH_CUDA_TRY(cudaMemcpyAsync(c->d_in + off, in + off, size_t(cuts[k + 1] - cuts[k]), cudaMemcpyHostToDevice, c->copy_in));
+    GH_CUDA_TRY(cudaEventRecord(c->ev_in[k], c->copy_in));
+  }
+  uint32_t entry = uint32_t(hdr - base) * 8;
+  uint64_t total = 0;
+  bool done = false, overflow = false;
+  for (size_t k = 0; k < nchunks && !done; ++k) {
+    const uint64_t left = stream_bytes - cuts[k];
+    const uint64_t slice = cuts[k + 1] - cuts[k];
+    const uint64_t readable = left < slice + kHostHalo ? left : slice + kHostHalo;
+    // the chunk and the halo it may read (the head of the next chunk) are on the device
+    GH_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[k + 1 < nchunks ? k + 1 : k], 0));
+    const uint8_t* d = c->d_in + base + cuts[k];
+    gh_shard_sync res;
+    rc = gh_decode_sync(d, slice, readable, &code, entry, 1, &res, c->d_ws, c->ws_cap, c->stream);
+    if (rc != GH_OK) return rc;
+    const uint64_t nsym = res.n_symbols;
+    if (overflow || nsym > cap - total) overflow = true;  // as gh_decode: keep counting, write nothing more
+    if (nsym && !overflow) {
+      rc = gh_decode_write(d, slice, readable, &code, c->d_out + total, nsym, c->d_ws, c->ws_cap, c->stream);
+      if (rc != GH_OK) return rc;
+      GH_CUDA_TRY(cudaEventRecord(c->ev_dec[k & 1], c->stream));
+      GH_CUDA_TRY(cudaStreamWaitEvent(c->copy_out, c->ev_dec[k & 1], 0));
+      GH_CUDA_TRY(cudaMemcpyAsync(out + total, c->d_out + total, size_t(nsym), cudaMemcpyDeviceToHost, c->copy_out));
+    }
+    total += nsym;
+    entry = res.exit_bit;
+    done = res.eof_found != 0;
+  }
+  *out_bytes = total;
+  GH_CUDA_TRY(cudaStreamSynchronize(c->copy_out));
   GH_CUDA_TRY(cudaStreamSynchronize(c->stream));
-  return GH_OK;
+  if (!done) return GH_ERR_NO_EOF;
+  return overflow ? GH_ERR_SPACE : GH_OK;
 }
 
 

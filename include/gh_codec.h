@@ -194,6 +194,10 @@ int gh_ctx_set_stream(gh_ctx* ctx, void* stream);
  * histogram -> code -> header -> packing back to back on the stream, with ONE read-back at the end; 0 (default):
  * the histogram is read back and the code is built on the host (gh_build_code). Same image either way. */
 int gh_ctx_set_device_code(gh_ctx* ctx, int on);
+/* gh_decompress_host moves the payload up and the decoded bytes back in chunks, on two copy engines beside the
+ * kernels (chunk k+1 uploads and chunk k-1 reads back while chunk k decodes). `bytes` = payload bytes per chunk
+ * (rounded up to 4 KiB; 0 = the default, 64 MiB). The decoded bytes do not depend on it. */
+int gh_ctx_set_host_chunk(gh_ctx* ctx, uint64_t bytes);
 
 uint64_t gh_compress_bound(uint64_t n); /* 1040 + 8*32 + 4*n + 32 */
 int gh_compress_host(gh_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_bytes);

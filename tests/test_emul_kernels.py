@@ -425,6 +425,38 @@ def test_emulated_compress_with_device_code(emu, oracle):
         emu.ctx_destroy(c)
 
 
+def test_emulated_host_decompress_in_chunks(emu, oracle):
+    """gh_decompress_host cuts the payload into chunks that decode in order (each from the previous one's exit bit): with
+    4 KiB and 12 KiB chunks the bytes are those of the one-chunk decode, the symbol count survives a too small output
+    buffer, and a truncated image is still reported as such"""
+    import golden_huffman_b200 as gh
+    rng = np.random.default_rng(11)
+    cases = [make_input("text_small") * 9,
+             np.minimum(rng.geometric(0.08, 70001), 255).astype(np.uint8).tobytes(),
+             bytes(range(256)) * 150 + b"\x07"]                       # {8, 9}-bit code: the phase walk in every chunk
+    c = emu.ctx_create()
+    try:
+        for data in cases:
+            n = len(data)
+            rc, img = oracle.compress(data)
+            assert rc == 0
+            src = np.frombuffer(img, dtype=np.uint8).copy()
+            for chunk in (4096, 12288, 131072, 0):
+                emu.ctx_set_host_chunk(c, chunk)
+                out = np.zeros(n + 8, dtype=np.uint8)
+                nd, rc = emu.decompress_host(c, src.ctypes.data, len(img), out.ctypes.data, n + 8)
+                assert rc == 0 and nd == n and out[:n].tobytes() == data, (chunk, n)
+            emu.ctx_set_host_chunk(c, 4096)
+            small = np.zeros(n - 5000, dtype=np.uint8)
+            nd, rc = emu.decompress_host(c, src.ctypes.data, len(img), small.ctypes.data, n - 5000, allow=(gh.capi.GH_ERR_SPACE,))
+            assert rc == gh.capi.GH_ERR_SPACE and nd == n
+            out = np.zeros(n + 8, dtype=np.uint8)
+            nd, rc = emu.decompress_host(c, src.ctypes.data, len(img) - 4200, out.ctypes.data, n + 8, allow=(gh.capi.GH_ERR_NO_EOF,))
+            assert rc == gh.capi.GH_ERR_NO_EOF
+    finally:
+        emu.ctx_destroy(c)
+
+
 def _stream_file_roundtrip(lib, oracle, tmp_path, data, chunk, resident):
     """the streaming layer through the C ABI, as the adapters drive it: pass 1, code, header, pass 2; then decode"""
     libc = C.CDLL(None)

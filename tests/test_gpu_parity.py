@@ -243,6 +243,29 @@ def test_host_buffer_api(codec, oracle):
     assert rc == 0 and nd == n and torch.equal(back[:n], src)
 
 
+def test_host_decompress_pipeline(codec):
+    """gh_decompress_host's chunked pipeline (upload, decode and read-back of different chunks at once) at a size with
+    several default chunks, and with small chunks; pinned and pageable host buffers"""
+    import torch
+    import golden_huffman_b200.workloads as w
+    n = (200 << 20) + 12345
+    x = w.zipf_torch(n, "cuda", seed=21)
+    img = codec.compress(x)
+    nb = img.numel()
+    src = img.cpu().pin_memory()
+    want = x.cpu()
+    try:
+        for chunk, pinned in ((0, True), (1 << 20, True), (0, False), (5 << 20, False)):
+            codec.lib.ctx_set_host_chunk(codec.ctx, chunk)
+            back = torch.empty(n + 8, dtype=torch.uint8)
+            back = back.pin_memory() if pinned else back
+            s = src if pinned else src.clone()
+            nd, rc = codec.decompress_host(s, nb, back)
+            assert rc == 0 and nd == n and torch.equal(back[:n], want), (chunk, pinned)
+    finally:
+        codec.lib.ctx_set_host_chunk(codec.ctx, 0)
+
+
 def test_error_statuses(codec, oracle):
     import torch
     import golden_huffman_b200 as gh

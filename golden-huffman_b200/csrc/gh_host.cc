@@ -2,7 +2,6 @@
 // small tables handed to the kernels. Pure C++ (no CUDA); microseconds per call.
 #include <string.h>
 
-#include <deque>
 #include <queue>
 #include <vector>
 
@@ -34,7 +33,11 @@ inline uint32_t get_be32(const uint8_t* p) {
 // survivor back with the summed weight. Follows include/canonical_huff_encoder.cc:289-345.
 int code_lengths(int64_t freq[GH_NSYM], uint32_t length[GH_NSYM], uint32_t* max_len) {
   int next_in_chain[GH_NSYM];
-  std::priority_queue<int, std::deque<int>, FreqGreater> heap((FreqGreater(freq)));
+  // the reference keeps the heap in a std::deque; the heap algorithms -- and with them the order among equal weights
+  // -- are the same for any random-access container, and a reserved vector is several times faster
+  std::vector<int> storage;
+  storage.reserve(GH_NSYM);
+  std::priority_queue<int, std::vector<int>, FreqGreater> heap((FreqGreater(freq)), std::move(storage));
   for (int s = 0; s < GH_NSYM; ++s) {
     if (freq[s]) heap.push(s);
     next_in_chain[s] = -1;

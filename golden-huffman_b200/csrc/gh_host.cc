@@ -166,14 +166,42 @@ int gh_parse_header(const uint8_t* src, size_t n, gh_code* code, size_t* header_
     code->start_pos[len] = get_be32(p);
     code->first_code[len] = get_be32(p + 4);
   }
-  // derive the encoder-side view (not stored in the file)
+  // The tables are redundant: all of them follow from the code lengths (do_gen_encode, include/canonical_huff_encoder.cc:
+  // 69-141). Only a header that is what the reference would have written for SOME set of lengths is accepted -- the
+  // decoders index symbol_[start_pos_[len] + code - first_code_[len]] and trust these numbers.
+  // (a) symbol_: the present symbols first, the rest is the reference's -1 fill
+  uint32_t present = 0;
+  while (present < GH_NSYM && code->symbol[present] < GH_NSYM) ++present;
+  for (uint32_t k = present; k < GH_NSYM; ++k)
+    if (code->symbol[k] != 0xFFFFFFFFu) return GH_ERR_FORMAT;
+  if (present < 2) return GH_ERR_FORMAT;  // a byte value and the end mark at least
+  // (b) start_pos_: where each length's symbols begin -> symbols per length
+  uint32_t per_len[GH_MAX_CODE_LEN + 2] = {0};
+  for (uint32_t len = 1; len <= code->max_len; ++len) {
+    const uint32_t lo = code->start_pos[len];
+    const uint32_t hi = len < code->max_len ? code->start_pos[len + 1] : present;
+    if (lo > present || hi > present || hi < lo) return GH_ERR_FORMAT;
+    if (len < code->min_len && hi != 0) return GH_ERR_FORMAT;
+    per_len[len] = hi - lo;
+  }
+  if (code->start_pos[1] != 0 || per_len[code->min_len] == 0 || per_len[code->max_len] == 0) return GH_ERR_FORMAT;
+  // (c) a Huffman code leaves no bit pattern unused: sum of 2^-len is exactly 1
+  uint64_t kraft = 0;
+  for (uint32_t len = 1; len <= code->max_len; ++len) kraft += uint64_t(per_len[len]) << (code->max_len - len);
+  if (kraft != (1ull << code->max_len)) return GH_ERR_FORMAT;
+  // (d) first_code_ as the reference derives it (entries below min_len hold its "never matches" mark: not compared)
+  uint32_t expect = 0;
+  for (uint32_t len = code->max_len; len >= code->min_len; --len) {
+    if (code->first_code[len] != expect) return GH_ERR_FORMAT;
+    expect = (expect + per_len[len]) / 2;
+  }
+  // (e) within a length the symbols ascend, and no symbol appears twice; this also derives the encoder-side view
+  // (not stored in the file)
   for (uint32_t len = code->min_len; len <= code->max_len; ++len) {
     const uint32_t lo = code->start_pos[len];
-    const uint32_t hi = len < code->max_len ? code->start_pos[len + 1] : GH_NSYM;
-    if (lo > GH_NSYM || hi > GH_NSYM || hi < lo) return GH_ERR_FORMAT;
-    for (uint32_t k = lo; k < hi; ++k) {
+    for (uint32_t k = lo; k < lo + per_len[len]; ++k) {
       const uint32_t s = code->symbol[k];
-      if (s >= GH_NSYM) break;
+      if (code->length[s] != 0 || (k > lo && s <= code->symbol[k - 1])) return GH_ERR_FORMAT;
       code->length[s] = len;
       code->codeword[s] = code->first_code[len] + (k - lo);
     }

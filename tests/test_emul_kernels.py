@@ -425,6 +425,21 @@ def test_emulated_compress_with_device_code(emu, oracle):
         emu.ctx_destroy(c)
 
 
+def test_emulated_histogram_epochs(emu):
+    """K1 counts in 16-bit halves of its shared-memory bins and folds them every 4088 vectors per thread: an input long
+    enough for two folds on the shim's two SMs, once with a single byte value (the counters' worst case), once random,
+    and from a misaligned address"""
+    n = 2 * 448 * 4088 * 16 + 5_000_001
+    rng = np.random.default_rng(1)
+    for fill in (7, None):
+        d = aligned(n + 16)
+        d[:n] = fill if fill is not None else rng.integers(0, 256, n, dtype=np.uint8)
+        h = aligned(256, np.uint64)
+        for off in (0, 3):
+            emu.histogram(d.ctypes.data + off, n - off, h.ctypes.data)
+            assert (h == np.bincount(d[off:n], minlength=256).astype(np.uint64)).all(), (fill, off)
+
+
 def test_emulated_host_decompress_in_chunks(emu, oracle):
     """gh_decompress_host cuts the payload into chunks that decode in order (each from the previous one's exit bit): with
     4 KiB and 12 KiB chunks the bytes are those of the one-chunk decode, the symbol count survives a too small output

@@ -55,9 +55,6 @@ constexpr int kDecThreads = 256;   // threads per block = subsequences per tile,
 #ifndef GH_DEC_S_BLOCKS
 #define GH_DEC_S_BLOCKS 6
 #endif
-#ifndef GH_DEC_W_BLOCKS
-#define GH_DEC_W_BLOCKS 4
-#endif
 constexpr u32 kNoEof = 0xffffffffu;
 constexpr u32 kEofPosUnknown = 0xfffffffeu;
 constexpr u32 kMinSubBytes = 128;
@@ -971,75 +968,101 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
 }
 
 // ---- K7: final decode from the exact entries ------------------------------------------------------------------
-// The cursor reader with the 13-bit table lutW: one LDS.64 yields the cursor/fill addend and up to 4 symbols.
-// `acc` carries, above the cursor byte, the number of output BITS produced so far (modulo 2^24), so the same IADD
-// that moves the cursor also advances the output fill; the symbols are shifted to the fill position (SHF takes
-// acc >> 9 modulo 32) and OR-ed into the word being assembled. A word is complete when bit 5 of the fill flips
-// (it joins a four-register queue), four words are complete when bit 7 flips (one 128-bit store): both are one
-// LOP3 on acc ^ acc_before. Everything between two stores is predicated straight-line code.
-struct SmemWrite {
+// The cursor reader with the table lutW: one LDS yields the cursor/fill addend and up to 2 (4) symbols. `acc` carries,
+// above the cursor field, the number of output BITS produced so far (modulo 2^22), so the same add that moves the
+// cursor also advances the output fill; the symbols are shifted to the fill position (SHF takes acc >> 10 modulo 32)
+// and OR-ed into the word being assembled. A word is complete when bit 5 of the fill flips -- one LOP3 on
+// acc ^ acc_before -- and then goes to the lane's private ring in shared memory (one predicated STS and one add).
+// The lookup loop is bound by its instruction stream (profiles/rnd2_notes.md), so everything else about the output
+// -- 16-byte grouping, the 64-bit destination, the global stores -- happens outside it: between two word steps, when
+// any lane of the warp may run out of ring space during the next step, every lane copies its ring to its own
+// destination with 128-bit loads and stores (a short loop in which all lanes work).
+// Two instances: rings of 32 words, three blocks per SM (the default), and rings of 16 words, four blocks per SM, for codes
+// without short codewords (min_len >= kSmallRingMinLen): those complete at most three words per step, and their lanes
+// run in lockstep -- measured on uniform bytes, the small rings' shorter store bursts and the fourth block win
+// (1.32 against 1.41 ms), while everything else prefers the large ones (Zipf 1.15 against 1.25 ms).
+// A word step completes at most (32 + kLutWBits - 1) / min_len symbols (its lookups consume at most that many bits)
+// plus the symbol of a table miss.
+__host__ __device__ constexpr u32 ring_step_words(u32 min_len) { return (u32(32 + kLutWBits - 1) / min_len + 3u) / 4u + 1u; }
+constexpr u32 kSmallRingMinLen = 7;
+template <int kRingWords>
+struct SmemWriteT {
+  static constexpr int kWords = kRingWords;       // usable words of a lane's ring
+  static constexpr int kStride = kRingWords + 4;  // in words: rows stay 16-byte aligned and start in different bank groups
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
   LutWEntry lutW[1 << kLutWBits];
   u32 warp_total[kDecThreads / 32];
+  alignas(16) u32 ring[kDecThreads * kStride];
 };
+struct WriteLarge {
+  typedef SmemWriteT<32> Smem;
+  static constexpr int kBlocksPerSm = 3;
+};
+struct WriteSmall {
+  typedef SmemWriteT<16> Smem;
+  static constexpr int kBlocksPerSm = 4;
+};
+static_assert(ring_step_words(1) < 32 && ring_step_words(kSmallRingMinLen) < 16, "ring too small for one word step");
 
-// Output queue of the write loop, branch-free: if `word_done`, the assembled word `merged` is shifted into the
-// four-register queue and `spill` opens the next word; if `group_done`, the queue leaves as one 128-bit store to
-// the lane's 16-byte-aligned destination (ghi:glo), which then advances. Written as predicated PTX: as C++
-// branches the compiler turns these few moves into divergent control flow that every warp then walks on almost
-// every iteration; and as predicated MOVs (not SEL) so that ptxas may place them on the FMA pipe -- the loop's
-// shifts and logic ops already fill the ALU pipe (each pipe issues a warp instruction every other cycle).
-__device__ __forceinline__ void queue_push_store(u32& q0, u32& q1, u32& q2, u32& q3, u32& part, u32 merged, u32 spill,
-                                                 u32 word_done, u32 group_done, u32& glo, u32& ghi, u32 one) {
-  (void)one;  // a register holding 1 that ptxas cannot see through: `x * one` is a move on the FMA pipe
+// `merged` becomes the open word; if `word_done`, it goes to the ring and `spill` opens the next one. Predicated PTX:
+// as C++ branches the compiler turns these few moves into divergent control flow that every warp then walks on almost
+// every iteration.
+__device__ __forceinline__ void ring_push(smem_addr_t& ring_at, u32& part, u32 merged, u32 spill, u32 word_done) {
 #ifdef GH_EMUL
   if (word_done) {
-    q0 = q1, q1 = q2, q2 = q3, q3 = merged;
+    *reinterpret_cast<u32*>(const_cast<char*>(ring_at)) = merged;
+    ring_at += 4;
     part = spill;
   } else {
     part = merged;
-  }
-  if (group_done) {
-    const u64 a = (u64(ghi) << 32) | glo;
-    *reinterpret_cast<uint4*>(a) = make_uint4(q0, q1, q2, q3);
-    glo = u32(a + 16), ghi = u32((a + 16) >> 32);
   }
 #else
   part = merged;
   asm volatile(
       "{\n"
-      " .reg .pred pw, pg;\n"
-      " .reg .u64 a;\n"
-      " setp.ne.u32 pw, %8, 0;\n"
-      " setp.ne.u32 pg, %9, 0;\n"
-      " @pw mad.lo.u32 %0, %1, %10, 0;\n"
-      " @pw mad.lo.u32 %1, %2, %10, 0;\n"
-      " @pw mad.lo.u32 %2, %3, %10, 0;\n"
-      " @pw mad.lo.u32 %3, %4, %10, 0;\n"
-      " @pw mov.u32 %4, %7;\n"
-      " mov.b64 a, {%5, %6};\n"
-      " @pg st.global.v4.u32 [a], {%0, %1, %2, %3};\n"
-      " @pg add.cc.u32 %5, %5, 16;\n"
-      " @pg addc.u32 %6, %6, 0;\n"
+      " .reg .pred pw;\n"
+      " setp.ne.u32 pw, %4, 0;\n"
+      " @pw st.shared.u32 [%0], %2;\n"
+      " @pw add.u32 %0, %0, 4;\n"
+      " @pw mov.u32 %1, %3;\n"
       "}\n"
-      : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3), "+r"(part), "+r"(glo), "+r"(ghi)
-      : "r"(spill), "r"(word_done), "r"(group_done), "r"(one)
+      : "+r"(ring_at), "+r"(part)
+      : "r"(merged), "r"(spill), "r"(word_done)
       : "memory");
 #endif
 }
 
-// bytes [from, to) of the 16-byte group (q0, q1, q2, q3) -> dst[from .. to): the unaligned head and the tail of a
-// lane's output (once per subsequence each)
-__device__ __noinline__ void store_group_bytes(uint8_t* dst, u32 q0, u32 q1, u32 q2, u32 q3, u32 from, u32 to) {
-  for (u32 b = from; b < to; ++b) {
-    const u32 w = (b >> 2) == 0 ? q0 : (b >> 2) == 1 ? q1 : (b >> 2) == 2 ? q2 : q3;
-    dst[b] = uint8_t(w >> (8 * (b & 3)));
-  }
+__device__ __forceinline__ uint4 ring_load4(smem_addr_t at) {
+#ifdef GH_EMUL
+  return *reinterpret_cast<const uint4*>(at);
+#else
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at));
+  return v;
+#endif
+}
+__device__ __forceinline__ u32 ring_load(smem_addr_t at) {
+#ifdef GH_EMUL
+  return *reinterpret_cast<const u32*>(at);
+#else
+  u32 v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(at));
+  return v;
+#endif
+}
+__device__ __forceinline__ void ring_store(smem_addr_t at, u32 v) {
+#ifdef GH_EMUL
+  *reinterpret_cast<u32*>(const_cast<char*>(at)) = v;
+#else
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(v) : "memory");
+#endif
 }
 
-__global__ void __launch_bounds__(kDecThreads, GH_DEC_W_BLOCKS)
+template <class Cfg>
+__global__ void __launch_bounds__(kDecThreads, Cfg::kBlocksPerSm)
 dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorkspace ws) {
+  typedef typename Cfg::Smem SmemWrite;
   GH_DYNAMIC_SMEM(smem_raw);
   SmemWrite& s = *reinterpret_cast<SmemWrite*>(smem_raw);
   load_canon(s.canon, ws.tables);
@@ -1064,45 +1087,64 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
   for (int k = 0; k < kDecThreads / 32; ++k)
     if (unsigned(k) < warp) warp_base += s.warp_total[k];
   const u64 o = ws.tile_base[blockIdx.x] + warp_base + (incl - count);
-  if (count == 0 || o >= out_cap) return;
-  u32 remaining = count;
-  if (u64(remaining) > out_cap - o) remaining = u32(out_cap - o);
-
-  const u64 start = i * u64(g.sub_bytes) * 8;
-  const u32 end = u32(sub_end_bits(g, i));
-  u32 pos = st_entry(st);  // bits of the subsequence consumed so far
-  uint8_t* dst = out + o;
+  // no early exit: the bulk loop below is warp-synchronous (its ring flushes are decided by a vote)
+  const bool live = count != 0 && o < out_cap;
+  u32 remaining = 0, end = 0, pos = 0;
+  u64 start = 0;
+  uint8_t* dst = out;
   u32 sym, len;
-  // head: single symbols up to the first 16-byte boundary of the output (the bytes before it belong to the
-  // previous lane), so that the bulk loop below only ever issues whole aligned 128-bit stores
-  if (reinterpret_cast<uintptr_t>(dst) & 15) {
-    BitReader r;
-    r.seek(g.payload, g.readable, start + pos);
-    while (remaining && (reinterpret_cast<uintptr_t>(dst) & 15)) {
-      decode_one(s.canon, s.lut1, r.window(), sym, len);
-      r.consume(len);
-      pos += len;
-      *dst++ = uint8_t(sym);
-      --remaining;
+  if (live) {
+    remaining = count;
+    if (u64(remaining) > out_cap - o) remaining = u32(out_cap - o);
+    start = i * u64(g.sub_bytes) * 8;
+    end = u32(sub_end_bits(g, i));
+    pos = st_entry(st);  // bits of the subsequence consumed so far
+    dst = out + o;
+    // head: single symbols up to the first 16-byte boundary of the output (the bytes before it belong to the
+    // previous lane), so that the bulk loop below only ever issues whole aligned 128-bit stores
+    if (reinterpret_cast<uintptr_t>(dst) & 15) {
+      BitReader r;
+      r.seek(g.payload, g.readable, start + pos);
+      while (remaining && (reinterpret_cast<uintptr_t>(dst) & 15)) {
+        decode_one(s.canon, s.lut1, r.window(), sym, len);
+        r.consume(len);
+        pos += len;
+        *dst++ = uint8_t(sym);
+        --remaining;
+      }
     }
   }
   // bulk: every codeword that starts before `end` belongs to this lane (that is what `count` counted), so the loop
   // is bounded by the bit position alone; a lane whose output was clipped by out_cap takes the slow path only.
   {
     typedef CursorGeom<kLutWBits, kLutWEntryShift> G;
-    u64 u, ulast;
-    u32 acc;
-    if (remaining && u64(count) <= out_cap - o && pos < end &&
-        cursor_plan<kLutWBits, kLutWEntryShift>(start + pos, start + end, g.readable >> 5, u, ulast, acc)) {
+    u64 u = 0, ulast = 0;
+    u32 acc = 0;
+    const bool bulk = live && remaining && u64(count) <= out_cap - o && pos < end &&
+                      cursor_plan<kLutWBits, kLutWEntryShift>(start + pos, start + end, g.readable >> 5, u, ulast, acc);
+    const u32 n_units = bulk ? u32(ulast - u) + 1u : 0u;
+    __syncwarp();
+    u32 n_units_warp = n_units;  // the warp walks together: lanes with fewer units idle through the rest
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const u32 other = __shfl_xor_sync(0xffffffffu, n_units_warp, d);
+      n_units_warp = other > n_units_warp ? other : n_units_warp;
+    }
+    if (n_units_warp) {
+      constexpr u32 kIdle = 192u;  // a cursor field that stays below the allowed range for a whole unit (8 x 32 more)
       const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
       const u64 umax = (g.readable >> 5) - 1;
       const smem_addr_t lut = smem_addr(s.lutW);
-      // destination of the next 128-bit store (16-byte aligned), as two words so the advance can be predicated
-      u32 glo = u32(reinterpret_cast<uintptr_t>(dst)), ghi = u32(u64(reinterpret_cast<uintptr_t>(dst)) >> 32);
-      const u32 one = blockDim.x / kDecThreads;  // 1, but not to ptxas: `x * one` stays a move on the FMA pipe
-      u32 q0 = 0, q1 = 0, q2 = 0, q3 = 0, part = 0;
+      const smem_addr_t ring0 = smem_addr(s.ring + t * SmemWrite::kStride);
+      // at or beyond `ring_full`, flush before the next step
+      const smem_addr_t ring_full = ring0 + 4 * (u32(SmemWrite::kWords) - ring_step_words(s.canon.min_len));
+      smem_addr_t ring_at = ring0;
+      u64 gaddr = u64(reinterpret_cast<uintptr_t>(dst));  // destination of the ring's first word (16-byte aligned)
+      u32 part = 0;
       u32 hi, lo = 0;
-      bool stop = false;  // the end mark was met (the subsequence that ends the stream)
+      bool stop = false;      // the end mark was met (the subsequence that ends the stream)
+      u32 acc_end = acc;      // the cursor after this lane's last unit
+      u32 units_left = n_units;
       auto append = [&](u32 addend, u32 syms) {
         const u32 fill = __umulhi(acc, 1u << (32 - kCurShift));  // acc >> kCurShift on the FMA pipe; SHF uses it modulo 32
         const u32 merged = part | __funnelshift_l(0u, syms, fill);
@@ -1110,10 +1152,17 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         const u32 next = acc + addend;
         const u32 flipped = next ^ acc;
         acc = next;
-        // a word is complete when bit 5 of the fill flipped: it joins the queue, the overflow opens the next one;
-        // four words are complete when bit 7 flipped: one 128-bit store. Predicated, no branches.
-        queue_push_store(q0, q1, q2, q3, part, merged, spill, flipped & (32u << kCurShift),
-                         flipped & (128u << kCurShift), glo, ghi, one);
+        ring_push(ring_at, part, merged, spill, flipped & (32u << kCurShift));  // bit 5 of the fill flipped: word complete
+      };
+      auto flush = [&]() {  // whole 16-byte groups leave; up to three words stay and move to the front
+        const u32 bytes = u32(ring_at - ring0);
+        const u32 n4 = bytes >> 4;
+        for (u32 k = 0; k < n4; ++k) *reinterpret_cast<uint4*>(gaddr + 16ull * k) = ring_load4(ring0 + 16 * k);
+        const u32 rest = bytes & 15u;
+        if (n4)
+          for (u32 k = 0; k < rest; k += 4) ring_store(ring0 + k, ring_load(ring0 + 16 * n4 + k));
+        gaddr += 16ull * n4;
+        ring_at = ring0 + rest;
       };
       auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {  // cu in stream order, the next unit's word raw
 #pragma unroll
@@ -1139,38 +1188,57 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
             const u32 sl = decode_one_packed(&s.canon, s.lut1, cursor_window32<kLutWBits, kLutWEntryShift>(hi, lo, next_be, acc));
             if ((sl >> 8) == u32(GH_EOF_SYMBOL)) {
               stop = true;
-              acc = (acc & ~kCurFieldMask) | 192u;  // stays below the allowed range for the rest of this unit
+              acc_end = acc;
+              acc = (acc & ~kCurFieldMask) | kIdle;
               break;
             }
             append((8u << kCurShift) - (sl & 0xffu), sl >> 8);
           }
+          if (__any_sync(0xffffffffu, ring_at >= ring_full)) flush();
         }
       };
-      // two unit buffers that swap roles, so the unit in flight is never copied (a copy would wait for the load)
-      Unit8 ua = ldg_unit(g.payload + 32 * u, aligned32), ub;
-      while (true) {
+      // One unit: a lane that has units left walks it, the others idle through it (their cursor field never reaches
+      // the allowed range). Two unit buffers swap roles, so the unit in flight is never copied (a copy would wait for
+      // the load).
+      auto begin_unit = [&]() -> bool {
+        const bool mine = units_left != 0u && !stop;
+        if (!mine) acc = (acc & ~kCurFieldMask) | kIdle;
+        return mine;
+      };
+      auto end_unit = [&](bool mine) {
+        if (mine && !stop) {
+          --units_left;
+          if (units_left == 0u) acc_end = acc;
+          else ++u;
+        }
+      };
+      if (!bulk) acc = kIdle;
+      Unit8 ua = ldg_unit(g.payload + 32 * (u < umax ? u : umax), aligned32), ub;
+      for (u32 it = 0; it < n_units_warp; it += 2) {
         unit_to_stream_order(ua);
         ub = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        bool mine = begin_unit();
         walk_unit(ua, ub.w[0]);
-        if (stop || u == ulast) break;
-        ++u;
+        end_unit(mine);
+        if (it + 1 >= n_units_warp) break;
         unit_to_stream_order(ub);
         ua = ldg_unit(g.payload + 32 * (u + 1 < umax ? u + 1 : umax), aligned32);
+        mine = begin_unit();
         walk_unit(ub, ua.w[0]);
-        if (stop || u == ulast) break;
-        ++u;
+        end_unit(mine);
       }
-      // drain: the open 16-byte group holds (fill mod 128) bits: completed words at the top of the queue, then `part`
-      const u32 fill = acc >> kCurShift;
-      const u32 open_bits = fill & 127u;
-      const u32 done_words = open_bits >> 5;
-      for (u32 k = done_words; k < 4; ++k) q0 = q1, q1 = q2, q2 = q3, q3 = (k == done_words ? part : 0u);
-      uint8_t* const gdst = reinterpret_cast<uint8_t*>((u64(ghi) << 32) | glo);
-      store_group_bytes(gdst, q0, q1, q2, q3, 0, open_bits >> 3);
-      const u64 emitted = u64(gdst - dst) + (open_bits >> 3);
-      dst += emitted;
-      remaining = stop ? 0u : remaining - u32(emitted);
-      pos = u32(cursor_position<kLutWBits, kLutWEntryShift>(ulast, acc) - start);
+      if (bulk) {
+        // drain: the ring's words, then the bytes of the open word
+        const u32 words = u32(ring_at - ring0) >> 2;
+        for (u32 k = 0; k < words; ++k) *reinterpret_cast<u32*>(gaddr + 4ull * k) = ring_load(ring0 + 4 * k);
+        uint8_t* tail = reinterpret_cast<uint8_t*>(gaddr + 4ull * words);
+        const u32 open_bytes = ((acc >> kCurShift) & 31u) >> 3;
+        for (u32 k = 0; k < open_bytes; ++k) tail[k] = uint8_t(part >> (8 * k));
+        const u64 emitted = u64(tail - dst) + open_bytes;
+        dst += emitted;
+        remaining = stop ? 0u : remaining - u32(emitted);
+        pos = u32(cursor_position<kLutWBits, kLutWEntryShift>(ulast, acc_end) - start);
+      }
     }
   }
   // what the bulk loop left (the last few bits of the subsequence, the payload tail, clipped output): one codeword
@@ -1454,7 +1522,8 @@ static bool g_no_phase_walk = false;  // gh_debug_disable_phase_walk: tests forc
 // Kernels that need more than the 48 KB of dynamic shared memory a kernel gets without opting in. The attribute is
 // per device, so it is set on every call (it costs nothing) rather than once per process.
 static int set_write_attrs() {
-  GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(SmemWrite))));
+  GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_kernel<WriteLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(WriteLarge::Smem))));
+  GH_CUDA_TRY(cudaFuncSetAttribute(dec_write_kernel<WriteSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(WriteSmall::Smem))));
   return GH_OK;
 }
 
@@ -1816,7 +1885,7 @@ static int decode_sync_impl(const uint8_t* d_payload, u64 slice_bytes, u64 reada
   return GH_OK;
 }
 
-static int decode_write_impl(const DecGeometry& g, bool fine, uint8_t* d_out, u64 out_cap, void* d_ws,
+static int decode_write_impl(const DecGeometry& g, u32 min_len, bool fine, uint8_t* d_out, u64 out_cap, void* d_ws,
                              cudaStream_t stream) {
   const DecLayout L = dec_layout(g.slice_bits / 8);
   DecWorkspace ws = dec_bind(d_ws, L);
@@ -1833,7 +1902,10 @@ static int decode_write_impl(const DecGeometry& g, bool fine, uint8_t* d_out, u6
   int rc = set_write_attrs();
   if (rc != GH_OK) return rc;
   const unsigned tiles = unsigned((g.n_sub + kDecThreads - 1) / kDecThreads);
-  GH_LAUNCH(dec_write_kernel, tiles, kDecThreads, sizeof(SmemWrite), stream, g, d_out, out_cap, ws);
+  if (min_len >= kSmallRingMinLen)
+    GH_LAUNCH(dec_write_kernel<WriteSmall>, tiles, kDecThreads, sizeof(WriteSmall::Smem), stream, g, d_out, out_cap, ws);
+  else
+    GH_LAUNCH(dec_write_kernel<WriteLarge>, tiles, kDecThreads, sizeof(WriteLarge::Smem), stream, g, d_out, out_cap, ws);
   return check_launch();
 }
 
@@ -1880,7 +1952,7 @@ int gh_decode_write(const uint8_t* d_payload, uint64_t slice_bytes, uint64_t rea
   g.n_sub = h_ctl.n_sub;
   g.entry0 = 0;
   if (g.sub_bytes < kMinSubBytes || g.n_sub != (slice_bytes + g.sub_bytes - 1) / g.sub_bytes) return GH_ERR_ARG;
-  return decode_write_impl(g, h_ctl.fine != 0, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+  return decode_write_impl(g, code->min_len, h_ctl.fine != 0, d_out, out_cap, d_workspace, (cudaStream_t)stream);
 }
 
 int gh_decode(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code* code, uint8_t* d_out,
@@ -1903,7 +1975,7 @@ int decode_full(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code*
   int rc = decode_sync_impl(d_payload, payload_bytes, payload_bytes, code, entry_bit, 1, &res, d_workspace,
                             workspace_bytes, (cudaStream_t)stream, &g, &fine, &deferred);
   if (rc != GH_OK) return rc;
-  rc = decode_write_impl(g, fine, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+  rc = decode_write_impl(g, code->min_len, fine, d_out, out_cap, d_workspace, (cudaStream_t)stream);
   if (rc != GH_OK) return rc;
   if (deferred) {
     const DecLayout L = dec_layout(payload_bytes);
@@ -1916,7 +1988,7 @@ int decode_full(const uint8_t* d_payload, uint64_t payload_bytes, const gh_code*
       rc = decode_sync_impl(d_payload, payload_bytes, payload_bytes, code, entry_bit, 1, &res, d_workspace, workspace_bytes,
                             (cudaStream_t)stream, &g, &fine, nullptr);
       if (rc != GH_OK) return rc;
-      rc = decode_write_impl(g, fine, d_out, out_cap, d_workspace, (cudaStream_t)stream);
+      rc = decode_write_impl(g, code->min_len, fine, d_out, out_cap, d_workspace, (cudaStream_t)stream);
       if (rc != GH_OK) return rc;
       GH_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     } else {

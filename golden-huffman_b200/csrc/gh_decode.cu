@@ -995,15 +995,21 @@ struct SmemWriteT {
   u32 warp_total[kDecThreads / 32];
   alignas(16) u32 ring[kDecThreads * kStride];
 };
+#ifndef GH_RING_LARGE
+#define GH_RING_LARGE 32  // tuning builds: other ring sizes / blocks per SM for the default instance
+#define GH_RING_LARGE_BLOCKS 3
+#endif
 struct WriteLarge {
-  typedef SmemWriteT<32> Smem;
-  static constexpr int kBlocksPerSm = 3;
+  typedef SmemWriteT<GH_RING_LARGE> Smem;
+  static constexpr int kBlocksPerSm = GH_RING_LARGE_BLOCKS;
+  static constexpr bool kFlushOutOfLine = true;
 };
 struct WriteSmall {
   typedef SmemWriteT<16> Smem;
   static constexpr int kBlocksPerSm = 4;
+  static constexpr bool kFlushOutOfLine = false;  // at 64 registers the call's saves and restores spill
 };
-static_assert(ring_step_words(1) < 32 && ring_step_words(kSmallRingMinLen) < 16, "ring too small for one word step");
+static_assert(ring_step_words(1) < GH_RING_LARGE && ring_step_words(kSmallRingMinLen) < 16, "ring too small for one word step");
 
 // `merged` becomes the open word; if `word_done`, it goes to the ring and `spill` opens the next one. Predicated PTX:
 // as C++ branches the compiler turns these few moves into divergent control flow that every warp then walks on almost
@@ -1058,6 +1064,28 @@ __device__ __forceinline__ void ring_store(smem_addr_t at, u32 v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(v) : "memory");
 #endif
 }
+
+// The copy-out of one lane's ring: whole 16-byte groups leave for `gaddr` (16-byte aligned), up to three words stay and
+// move to the front. Out of line where registers allow: it runs once per ~15 word steps, and inlined at all sixteen
+// word steps of the unrolled unit pair it is a quarter of the kernel's code.
+__device__ __forceinline__ void ring_flush_body(smem_addr_t ring0, u32 bytes, u64 gaddr) {
+  const u32 n4 = bytes >> 4;
+#pragma unroll 1
+  for (u32 k = 0; k < n4; ++k) {
+    const uint4 v = ring_load4(ring0 + 16 * k);
+#ifdef GH_EMUL
+    *reinterpret_cast<uint4*>(gaddr + 16ull * k) = v;
+#else
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gaddr + 16ull * k), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
+  }
+  const u32 rest = bytes & 15u;
+  if (n4) {
+#pragma unroll 1
+    for (u32 k = 0; k < rest; k += 4) ring_store(ring0 + k, ring_load(ring0 + 16 * n4 + k));
+  }
+}
+__device__ __noinline__ void ring_flush_call(smem_addr_t ring0, u32 bytes, u64 gaddr) { ring_flush_body(ring0, bytes, gaddr); }
 
 template <class Cfg>
 __global__ void __launch_bounds__(kDecThreads, Cfg::kBlocksPerSm)
@@ -1154,15 +1182,12 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         acc = next;
         ring_push(ring_at, part, merged, spill, flipped & (32u << kCurShift));  // bit 5 of the fill flipped: word complete
       };
-      auto flush = [&]() {  // whole 16-byte groups leave; up to three words stay and move to the front
+      auto flush = [&]() {
         const u32 bytes = u32(ring_at - ring0);
-        const u32 n4 = bytes >> 4;
-        for (u32 k = 0; k < n4; ++k) *reinterpret_cast<uint4*>(gaddr + 16ull * k) = ring_load4(ring0 + 16 * k);
-        const u32 rest = bytes & 15u;
-        if (n4)
-          for (u32 k = 0; k < rest; k += 4) ring_store(ring0 + k, ring_load(ring0 + 16 * n4 + k));
-        gaddr += 16ull * n4;
-        ring_at = ring0 + rest;
+        if constexpr (Cfg::kFlushOutOfLine) ring_flush_call(ring0, bytes, gaddr);
+        else ring_flush_body(ring0, bytes, gaddr);
+        gaddr += u64(bytes & ~15u);
+        ring_at = ring0 + (bytes & 15u);
       };
       auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {  // cu in stream order, the next unit's word raw
 #pragma unroll

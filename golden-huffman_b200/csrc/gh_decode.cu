@@ -976,7 +976,7 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
 // The lookup loop is bound by its instruction stream (profiles/rnd2_notes.md), so everything else about the output
 // -- 16-byte grouping, the 64-bit destination, the global stores -- happens outside it: between two word steps, when
 // any lane of the warp may run out of ring space during the next step, every lane copies its ring to its own
-// destination with 128-bit loads and stores (a short loop in which all lanes work).
+// destination, four words per 128-bit store (a short loop in which all lanes work).
 // Two instances: rings of 32 words, three blocks per SM (the default), and rings of 16 words, four blocks per SM, for codes
 // without short codewords (min_len >= kSmallRingMinLen): those complete at most three words per step, and their lanes
 // run in lockstep -- measured on uniform bytes, the small rings' shorter store bursts and the fourth block win
@@ -985,15 +985,18 @@ dec_offsets_kernel(DecGeometry g, DecWorkspace ws) {
 // plus the symbol of a table miss.
 __host__ __device__ constexpr u32 ring_step_words(u32 min_len) { return (u32(32 + kLutWBits - 1) / min_len + 3u) / 4u + 1u; }
 constexpr u32 kSmallRingMinLen = 7;
+// Word w of the ring of lane l of warp v sits at ring[(v * kWords + w) * 32 + l]: bank = lane for every access to the
+// rings, whatever the lanes' fill levels (rows per lane -- 128-bit loads in the copy-out, but 4 lanes per bank group --
+// cost 1-2 %, and a row stride of exactly 32 words 27 %).
+constexpr u32 kRingWordStep = 128;  // bytes from one word of a lane's ring to the next
 template <int kRingWords>
 struct SmemWriteT {
   static constexpr int kWords = kRingWords;       // usable words of a lane's ring
-  static constexpr int kStride = kRingWords + 4;  // in words: rows stay 16-byte aligned and start in different bank groups
   SmemCanon canon;
   uint16_t lut1[1 << kLut1Bits];
   LutWEntry lutW[1 << kLutWBits];
   u32 warp_total[kDecThreads / 32];
-  alignas(16) u32 ring[kDecThreads * kStride];
+  alignas(16) u32 ring[kDecThreads * kRingWords];
 };
 #ifndef GH_RING_LARGE
 #define GH_RING_LARGE 32  // tuning builds: other ring sizes / blocks per SM for the default instance
@@ -1018,7 +1021,7 @@ __device__ __forceinline__ void ring_push(smem_addr_t& ring_at, u32& part, u32 m
 #ifdef GH_EMUL
   if (word_done) {
     *reinterpret_cast<u32*>(const_cast<char*>(ring_at)) = merged;
-    ring_at += 4;
+    ring_at += kRingWordStep;
     part = spill;
   } else {
     part = merged;
@@ -1030,24 +1033,15 @@ __device__ __forceinline__ void ring_push(smem_addr_t& ring_at, u32& part, u32 m
       " .reg .pred pw;\n"
       " setp.ne.u32 pw, %4, 0;\n"
       " @pw st.shared.u32 [%0], %2;\n"
-      " @pw add.u32 %0, %0, 4;\n"
+      " @pw add.u32 %0, %0, %5;\n"
       " @pw mov.u32 %1, %3;\n"
       "}\n"
       : "+r"(ring_at), "+r"(part)
-      : "r"(merged), "r"(spill), "r"(word_done)
+      : "r"(merged), "r"(spill), "r"(word_done), "n"(kRingWordStep)
       : "memory");
 #endif
 }
 
-__device__ __forceinline__ uint4 ring_load4(smem_addr_t at) {
-#ifdef GH_EMUL
-  return *reinterpret_cast<const uint4*>(at);
-#else
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at));
-  return v;
-#endif
-}
 __device__ __forceinline__ u32 ring_load(smem_addr_t at) {
 #ifdef GH_EMUL
   return *reinterpret_cast<const u32*>(at);
@@ -1068,24 +1062,26 @@ __device__ __forceinline__ void ring_store(smem_addr_t at, u32 v) {
 // The copy-out of one lane's ring: whole 16-byte groups leave for `gaddr` (16-byte aligned), up to three words stay and
 // move to the front. Out of line where registers allow: it runs once per ~15 word steps, and inlined at all sixteen
 // word steps of the unrolled unit pair it is a quarter of the kernel's code.
-__device__ __forceinline__ void ring_flush_body(smem_addr_t ring0, u32 bytes, u64 gaddr) {
-  const u32 n4 = bytes >> 4;
+__device__ __forceinline__ void ring_flush_body(smem_addr_t ring0, u32 words, u64 gaddr) {
+  const u32 n4 = words >> 2;
 #pragma unroll 1
   for (u32 k = 0; k < n4; ++k) {
-    const uint4 v = ring_load4(ring0 + 16 * k);
+    const smem_addr_t at = ring0 + 4 * kRingWordStep * k;
+    const uint4 v = make_uint4(ring_load(at), ring_load(at + kRingWordStep), ring_load(at + 2 * kRingWordStep),
+                               ring_load(at + 3 * kRingWordStep));
 #ifdef GH_EMUL
     *reinterpret_cast<uint4*>(gaddr + 16ull * k) = v;
 #else
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gaddr + 16ull * k), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 #endif
   }
-  const u32 rest = bytes & 15u;
+  const u32 rest = words & 3u;
   if (n4) {
 #pragma unroll 1
-    for (u32 k = 0; k < rest; k += 4) ring_store(ring0 + k, ring_load(ring0 + 16 * n4 + k));
+    for (u32 k = 0; k < rest; ++k) ring_store(ring0 + kRingWordStep * k, ring_load(ring0 + kRingWordStep * (4 * n4 + k)));
   }
 }
-__device__ __noinline__ void ring_flush_call(smem_addr_t ring0, u32 bytes, u64 gaddr) { ring_flush_body(ring0, bytes, gaddr); }
+__device__ __noinline__ void ring_flush_call(smem_addr_t ring0, u32 words, u64 gaddr) { ring_flush_body(ring0, words, gaddr); }
 
 template <class Cfg>
 __global__ void __launch_bounds__(kDecThreads, Cfg::kBlocksPerSm)
@@ -1163,9 +1159,9 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
       const bool aligned32 = (reinterpret_cast<uintptr_t>(g.payload) & 31) == 0;
       const u64 umax = (g.readable >> 5) - 1;
       const smem_addr_t lut = smem_addr(s.lutW);
-      const smem_addr_t ring0 = smem_addr(s.ring + t * SmemWrite::kStride);
+      const smem_addr_t ring0 = smem_addr(s.ring + warp * 32 * SmemWrite::kWords + lane);
       // at or beyond `ring_full`, flush before the next step
-      const smem_addr_t ring_full = ring0 + 4 * (u32(SmemWrite::kWords) - ring_step_words(s.canon.min_len));
+      const smem_addr_t ring_full = ring0 + kRingWordStep * (u32(SmemWrite::kWords) - ring_step_words(s.canon.min_len));
       smem_addr_t ring_at = ring0;
       u64 gaddr = u64(reinterpret_cast<uintptr_t>(dst));  // destination of the ring's first word (16-byte aligned)
       u32 part = 0;
@@ -1183,11 +1179,11 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
         ring_push(ring_at, part, merged, spill, flipped & (32u << kCurShift));  // bit 5 of the fill flipped: word complete
       };
       auto flush = [&]() {
-        const u32 bytes = u32(ring_at - ring0);
-        if constexpr (Cfg::kFlushOutOfLine) ring_flush_call(ring0, bytes, gaddr);
-        else ring_flush_body(ring0, bytes, gaddr);
-        gaddr += u64(bytes & ~15u);
-        ring_at = ring0 + (bytes & 15u);
+        const u32 words = u32(ring_at - ring0) / kRingWordStep;
+        if constexpr (Cfg::kFlushOutOfLine) ring_flush_call(ring0, words, gaddr);
+        else ring_flush_body(ring0, words, gaddr);
+        gaddr += 4ull * (words & ~3u);
+        ring_at = ring0 + kRingWordStep * (words & 3u);
       };
       auto walk_unit = [&](const Unit8& cu, u32 next_unit_word0) {  // cu in stream order, the next unit's word raw
 #pragma unroll
@@ -1254,8 +1250,8 @@ dec_write_kernel(DecGeometry g, uint8_t* __restrict__ out, u64 out_cap, DecWorks
       }
       if (bulk) {
         // drain: the ring's words, then the bytes of the open word
-        const u32 words = u32(ring_at - ring0) >> 2;
-        for (u32 k = 0; k < words; ++k) *reinterpret_cast<u32*>(gaddr + 4ull * k) = ring_load(ring0 + 4 * k);
+        const u32 words = u32(ring_at - ring0) / kRingWordStep;
+        for (u32 k = 0; k < words; ++k) *reinterpret_cast<u32*>(gaddr + 4ull * k) = ring_load(ring0 + kRingWordStep * k);
         uint8_t* tail = reinterpret_cast<uint8_t*>(gaddr + 4ull * words);
         const u32 open_bytes = ((acc >> kCurShift) & 31u) >> 3;
         for (u32 k = 0; k < open_bytes; ++k) tail[k] = uint8_t(part >> (8 * k));
